@@ -1,0 +1,130 @@
+/* ---------------------------------------------------------------------------
+ * eulerb200.h -- C ABI of the B200-native fluid right-hand side
+ *                f_1(w) = G - div F(w)   (5th-order FD-WENO, Lax-Friedrichs splitting)
+ * of sundials-manyvector-demo.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point names the reference interface it stands in for; paths are
+ * relative to the reference tree, src/.
+ *
+ * Data layout (unchanged from the reference, euler3D.hpp:62,65):
+ *   w[0..4] = rho, mx, my, mz, et   each nxl*nyl*nzl doubles, index i + nxl*(j + nyl*k)
+ *   w[5]    = chem                  nxl*nyl*nzl*nchem doubles, index v + nchem*cell
+ * i.e. exactly the six sub-vector arrays N_VGetSubvectorArrayPointer_MPIManyVector
+ * returns (utilities.cpp:31-58).  Pointers are DEVICE (or managed) pointers unless the
+ * function name ends in _host.
+ *
+ * Return codes follow the reference / ARKODE convention (utilities.cpp:542-591):
+ *   0 success, <0 unrecoverable (-1: illegal state / invalid argument, -2: CUDA error,
+ *   -3: communication error).  eulerb200_last_error() gives the text.
+ * There is no CPU fallback: without a usable CUDA device eulerb200_create fails with -2.
+ * ------------------------------------------------------------------------- */
+#ifndef EULERB200_H
+#define EULERB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EULERB200_VERSION 100
+
+/* boundary condition codes: euler3D.hpp:90-93 */
+#define EULERB200_BC_PERIODIC   0
+#define EULERB200_BC_NEUMANN    1
+#define EULERB200_BC_DIRICHLET  2
+#define EULERB200_BC_REFLECTING 3
+
+/* face order everywhere: W, E, S, N, B, F  (x-low, x-high, y-low, y-high, z-low, z-high) */
+#define EULERB200_NO_NEIGHBOR (-1)   /* MPI_PROC_NULL: the face is a physical boundary */
+
+typedef struct eulerb200_ctx eulerb200_ctx;
+
+/* The fields of class EulerData the hot path reads (euler3D.hpp:177-270). */
+typedef struct eulerb200_config {
+  int64_t nxl, nyl, nzl;   /* local extents              euler3D.hpp:198-200 */
+  int32_t nchem;           /* NVAR-5                      euler3D.hpp:220,297 */
+  int32_t device;          /* CUDA device ordinal (-1: keep the current device) */
+  double dx, dy, dz;       /* mesh spacing                euler3D.hpp:209-211 */
+  double gamma;            /* ratio of specific heats     euler3D.hpp:221 */
+  int32_t bc[6];           /* xlbc,xrbc,ylbc,yrbc,zlbc,zrbc   euler3D.hpp:214-219 */
+  int32_t nbr[6];          /* ipW,ipE,ipS,ipN,ipB,ipF     euler3D.hpp:251-256;
+                              EULERB200_NO_NEIGHBOR for a physical boundary; == rank when the
+                              periodic wrap lands on this rank itself */
+  int32_t rank, nranks;    /* myid, nprocs                euler3D.hpp:246-247 */
+  double forcing[5];       /* constant G assigned into wdot: the external_forces hook
+                              (euler3D.hpp:1454); zero for every shipped problem except
+                              Rayleigh-Taylor's Gmy = -0.1 (rayleigh_taylor.cpp:117-128) */
+} eulerb200_config;
+
+int eulerb200_version(void);
+
+/* EulerData::SetupDecomp, the arithmetic part (euler3D.hpp:416-440,466-567):
+ * process grid from MPI_Dims_create over the axes with more than 3 cells, block extents
+ * by integer division, neighbour ranks of a non-reordered Cartesian communicator.
+ *   n[3] global cells, bc[6]; out: dims[3] = npx,npy,npz; coords[3];
+ *   ext[6] = is,ie,js,je,ks,ke; nbr[6] = ipW..ipF (EULERB200_NO_NEIGHBOR = MPI_PROC_NULL).
+ * Returns 0, 1 if only one boundary of an axis is periodic (euler3D.hpp:443-457),
+ * -1 if a local extent would be < 3 (euler3D.hpp:483-494). */
+int eulerb200_decompose(int32_t nprocs, int32_t rank, const int64_t* n, const int32_t* bc,
+                        int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr);
+
+/* EulerData constructor + the allocation part of SetupDecomp (euler3D.hpp:497-559):
+ * owns halo slabs, streams, events and the legal-state flag.  Never allocates afterwards. */
+int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out);
+/* EulerData::FreeData (euler3D.hpp:304-377) */
+int eulerb200_destroy(eulerb200_ctx* ctx);
+const char* eulerb200_last_error(const eulerb200_ctx* ctx);   /* ctx may be NULL: create errors */
+
+/* Multi-GPU transport (stands in for the Cartesian communicator of euler3D.hpp:461 and
+ * the Isend/Irecv pairs of euler3D.hpp:607-786).  One process per GPU.  Rank 0 obtains an
+ * id, the host distributes the 128 bytes by whatever means it has (MPI_Bcast in the
+ * reference drivers, torch.distributed in the tests), every rank attaches. */
+#define EULERB200_UNIQUE_ID_BYTES 128
+int eulerb200_comm_unique_id(void* id_bytes);
+int eulerb200_comm_attach(eulerb200_ctx* ctx, const void* id_bytes);
+
+/* fEuler (utilities.cpp:17-253): wdot = G - div F(w), including the halo exchange when
+ * the context has neighbours.  Enqueued on `stream` (a cudaStream_t, NULL = default).
+ * eulerb200_rhs returns only after the legal_state flag has been read back, like the
+ * reference: 0, or -1 if any owned cell has rho<=0, et<=0 or p<=0 (utilities.cpp:83-84).
+ * eulerb200_rhs_async does not synchronise; eulerb200_state_flag() later returns the
+ * flag bits (1 density, 2 energy, 4 pressure; check_flag opt 4, utilities.cpp:575-588). */
+int eulerb200_rhs(eulerb200_ctx* ctx, double t, const double* const* w, double* const* wdot,
+                  void* stream);
+int eulerb200_rhs_async(eulerb200_ctx* ctx, double t, const double* const* w, double* const* wdot,
+                        void* stream);
+int eulerb200_state_flag(eulerb200_ctx* ctx, void* stream, int32_t* bits);
+
+/* Same call with HOST arrays (what a driver holding serial N_Vectors has): stages
+ * host->device, evaluates, stages device->host, pipelined over z-slabs. */
+int eulerb200_rhs_host(eulerb200_ctx* ctx, double t, const double* const* w_host,
+                       double* const* wdot_host);
+
+/* EulerData::ExchangeStart / ExchangeEnd (euler3D.hpp:577-1191), callable on their own. */
+int eulerb200_exchange_start(eulerb200_ctx* ctx, const double* const* w, void* stream);
+int eulerb200_exchange_end(eulerb200_ctx* ctx, void* stream);
+/* Ghost layers of one face in the reference's receive-buffer layout (Wrecv..Frecv,
+ * euler3D.hpp:257-262, index v + NVAR*(d + 3*(a + na*b))), whatever their source
+ * (neighbour halo, periodic wrap, or boundary-condition fill euler3D.hpp:797-1166).
+ * dst is a device pointer to eulerb200_face_len() doubles.  Call after exchange_end. */
+int64_t eulerb200_face_len(const eulerb200_ctx* ctx, int32_t face);
+int eulerb200_ghost_face(eulerb200_ctx* ctx, const double* const* w, int32_t face, double* dst,
+                         void* stream);
+
+/* stability (utilities.cpp:483-528): dt = cfl*min(dx,dy,dz)/max_cells(| |mx/rho| + c |),
+ * max taken over all ranks.  Synchronous (returns the value). */
+int eulerb200_stability(eulerb200_ctx* ctx, const double* const* w, double cfl, double* dt_stab,
+                        void* stream);
+
+/* Number of kernel launches issued through this context so far. */
+int64_t eulerb200_launch_count(const eulerb200_ctx* ctx);
+
+/* Measurement aid (no reference counterpart): sustained DFMA throughput of the current
+ * device in TFLOP/s, the denominator of the FP64-pipe roofline bench.py reports. */
+int eulerb200_fp64_peak(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EULERB200_H */

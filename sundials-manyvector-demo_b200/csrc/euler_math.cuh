@@ -1,0 +1,196 @@
+// ---------------------------------------------------------------------------
+// euler_math.cuh -- face-flux arithmetic of the fluid RHS, written for the FP64 pipe.
+//
+// What the reference computes per face (face_flux, /root/reference/src/utilities.cpp:270-479)
+// is kept; how it is computed is reorganised so that one face costs ~750 FP64-pipe
+// instructions for the five fluid fields and ~100 per tracer instead of the
+// reference's ~1550 / ~150:
+//   * the 0.5 of the Lax-Friedrichs split (:388,:431) is folded out of the WENO input:
+//     WENO(0.5 g; eps) == 0.5 WENO(g; 4 eps) exactly (power-of-two scaling), so the
+//     split is g = F +- alpha*w and one 0.5 is applied to the sum f+ + f- at the end;
+//   * LV/RV (:312-364) are never formed: their structural zeros are skipped and the
+//     rows that share sub-expressions are evaluated together (13 ops per projection);
+//   * tracers: F +- alpha*w = (u +- alpha)*c  (identity projection, :395,:439,:473);
+//   * the three nonlinear weights are combined over a common denominator, so one
+//     reciprocal per reconstruction replaces the reference's four divisions (:408-422);
+//   * f- is f+ on the mirrored five points (:443-467 is :399-423 reflected).
+// Every one of these is an exact identity in real arithmetic; in FP64 they change
+// rounding at the 1e-16 level (the same size as letting the compiler contract FMAs in
+// the reference itself).  Quirks that matter for parity are
+// kept: c^2 without the square root in the eigenvectors (:309), the face-local 6-point
+// alpha (:368-380), SUNRsqrt's "non-positive -> 0" (:298-299,:378), epsilon added before
+// squaring (:408-410).
+//
+// The file is host/device so that tests can run exactly this arithmetic on the CPU
+// (tests/emu) against the oracle without a GPU.
+// ---------------------------------------------------------------------------
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define EB_HD __host__ __device__ __forceinline__
+#else
+#define EB_HD inline
+#endif
+
+namespace eb {
+
+// SUNRsqrt of SUNDIALS 6.2 (sundials_math.h): x <= 0 gives 0.
+EB_HD double sun_sqrt(double x) { return (x <= 0.0) ? 0.0 : sqrt(x); }
+
+// Reciprocal on the FP64 pipe: hardware seed + two Newton steps (about 1 ulp); the
+// full IEEE division sequence costs roughly twice as many FP64 issue slots.
+EB_HD double fast_rcp(double b)
+{
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / b;
+#endif
+}
+
+// Fifth-order WENO value at the face from five samples, left-biased ("f+") form of
+// utilities.cpp:399-423 applied to UNHALVED split fluxes (hence 4*epsilon).  Call with
+// the samples reversed for the right-biased ("f-") form.
+//   result = q2 + [ a1 (q1-q2) + a3 (q3-q2) ] / (a1+a2+a3),  a_k = d_k / (eps+beta_k)^2
+// with q1-q2 = -(D1-D2)/6 and q3-q2 = (D3-D2)/3 (D_k the second differences).
+EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
+{
+  const double bc = 13.0 / 12.0;
+  const double eps4 = 4.0 * 1e-6;
+  const double D1 = fma(-2.0, v3, v2) + v4;
+  const double D2 = fma(-2.0, v2, v1) + v3;
+  const double D3 = fma(-2.0, v1, v0) + v2;
+  const double E1 = fma(3.0, v2, fma(-4.0, v3, v4));
+  const double E2 = v1 - v3;
+  const double E3 = fma(3.0, v2, fma(-4.0, v1, v0));
+  const double b1 = fma(bc, D1 * D1, fma(0.25, E1 * E1, eps4));
+  const double b2 = fma(bc, D2 * D2, fma(0.25, E2 * E2, eps4));
+  const double b3 = fma(bc, D3 * D3, fma(0.25, E3 * E3, eps4));
+  const double s1 = b1 * b1, s2 = b2 * b2, s3 = b3 * b3;
+  const double P1 = s2 * s3, P2 = s1 * s3, P3 = s1 * s2;
+  const double den = fma(0.3, P1, fma(0.6, P2, 0.1 * P3));
+  const double num = fma((0.1 / 3.0) * P3, D3 - D2, (-0.3 / 6.0) * P1 * (D1 - D2));
+  const double q2 = fma(1.0 / 3.0, v3, fma(5.0 / 6.0, v2, (-1.0 / 6.0) * v1));
+  return fma(num, fast_rcp(den), q2);
+}
+
+// Roe-averaged face state and the projection coefficients derived from it.
+struct Eigen {
+  double u, v, w, H, q, cs;   // cs = (gamma-1)(H - q/2): c^2, NOT c (utilities.cpp:309)
+  double gc, hgc, hc;         // (gamma-1)/cs, half of it, 0.5/cs
+};
+
+// Characteristic projection y = LV x (utilities.cpp:342-364 with the zeros skipped).
+EB_HD void project(const Eigen& E, double x0, double x1, double x2, double x3, double x4,
+                   double& y0, double& y1, double& y2, double& y3, double& y4)
+{
+  const double S = fma(-E.w, x3, fma(-E.v, x2, fma(-E.u, x1, x4)));
+  const double C = E.hgc * fma(0.5 * E.q, x0, S);
+  const double D = E.hc * fma(E.u, x0, -x1);
+  y0 = C + D;
+  y4 = C - D;
+  y1 = fma(-E.v, x0, x2);
+  y2 = fma(-E.w, x0, x3);
+  y3 = -E.gc * fma(E.q - E.H, x0, S);
+}
+
+// Six-point stencil of the five fluid fields in sweep-aligned order: mn is the
+// momentum normal to the face, m1/m2 the tangential ones in the order the reference's
+// swap leaves them (utilities.cpp:283-285: x:(mx,my,mz)  y:(my,mx,mz)  z:(mz,my,mx)).
+struct FluidStencil {
+  double r[6], mn[6], m1[6], m2[6], e[6];
+};
+
+// Fluid part of one face.  Returns through `f` the five face fluxes in sweep-aligned
+// order (rho, normal, tan1, tan2, energy), and through alpha / u[6] what the tracers
+// of the same face need (face-local max wave speed, normal velocity per point); p3_out is
+// the pressure of stencil point 3 (the cell above the face), for the legal_state check.
+EB_HD void fluid_face(const FluidStencil& s, double gamma, double f[5], double& alpha_out, double u[6],
+                       double& p3_out)
+{
+  const double gm1 = gamma - 1.0;
+  double p[6];
+  double alpha = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const double rinv = fast_rcp(s.r[j]);
+    u[j] = s.mn[j] * rinv;
+    const double m2sum = fma(s.m2[j], s.m2[j], fma(s.m1[j], s.m1[j], s.mn[j] * s.mn[j]));
+    p[j] = gm1 * fma(-0.5 * m2sum, rinv, s.e[j]);
+    const double a = fabs(u[j]) + sun_sqrt(gamma * p[j] * rinv);
+    alpha = (alpha < a) ? a : alpha;
+  }
+  alpha_out = alpha;
+  p3_out = p[3];
+
+  // Roe average of the two cells adjacent to the face (utilities.cpp:298-304):
+  // 0.5*(a/sL + b/sR)/(0.5*(sL+sR)) = (a/sL + b/sR)/(sL+sR)
+  Eigen E;
+  {
+    const double sL = sun_sqrt(s.r[2]), sR = sun_sqrt(s.r[3]);
+    const double isL = fast_rcp(sL), isR = fast_rcp(sR), iS = fast_rcp(sL + sR);
+    E.u = fma(s.mn[2], isL, s.mn[3] * isR) * iS;
+    E.v = fma(s.m1[2], isL, s.m1[3] * isR) * iS;
+    E.w = fma(s.m2[2], isL, s.m2[3] * isR) * iS;
+    E.H = fma(p[2] + s.e[2], isL, (p[3] + s.e[3]) * isR) * iS;
+    E.q = fma(E.w, E.w, fma(E.v, E.v, E.u * E.u));
+    E.cs = gm1 * fma(-0.5, E.q, E.H);
+    const double cinv = fast_rcp(E.cs);
+    E.gc = gm1 * cinv;
+    E.hgc = 0.5 * E.gc;
+    E.hc = 0.5 * cinv;
+  }
+
+  // Split fluxes g+ (points 0..4) and g- (points 1..5), projected (utilities.cpp:386-396,429-440)
+  double gp[5][5], gm[5][5];   // [point][characteristic]
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const double F0 = s.mn[j];
+    const double F1 = fma(u[j], s.mn[j], p[j]);
+    const double F2 = u[j] * s.m1[j];
+    const double F3 = u[j] * s.m2[j];
+    const double F4 = u[j] * (s.e[j] + p[j]);
+    if (j < 5)
+      project(E, fma(alpha, s.r[j], F0), fma(alpha, s.mn[j], F1), fma(alpha, s.m1[j], F2),
+              fma(alpha, s.m2[j], F3), fma(alpha, s.e[j], F4),
+              gp[j][0], gp[j][1], gp[j][2], gp[j][3], gp[j][4]);
+    if (j > 0)
+      project(E, fma(-alpha, s.r[j], F0), fma(-alpha, s.mn[j], F1), fma(-alpha, s.m1[j], F2),
+              fma(-alpha, s.m2[j], F3), fma(-alpha, s.e[j], F4),
+              gm[j - 1][0], gm[j - 1][1], gm[j - 1][2], gm[j - 1][3], gm[j - 1][4]);
+  }
+
+  // WENO per characteristic field; 0.5 of the split applied once to f+ + f-
+  double ff[5];
+#pragma unroll
+  for (int c = 0; c < 5; c++)
+    ff[c] = 0.5 * (weno5(gp[0][c], gp[1][c], gp[2][c], gp[3][c], gp[4][c]) +
+                   weno5(gm[4][c], gm[3][c], gm[2][c], gm[1][c], gm[0][c]));
+
+  // Back to conserved variables: RV ff (utilities.cpp:318-340,470-472)
+  const double f0 = ff[0] + ff[3] + ff[4];
+  const double dl = ff[4] - ff[0];
+  f[0] = f0;
+  f[1] = fma(E.u, f0, E.cs * dl);
+  f[2] = fma(E.v, f0, ff[1]);
+  f[3] = fma(E.w, f0, ff[2]);
+  f[4] = fma(E.H, ff[0] + ff[4], fma(E.u * E.cs, dl, fma(E.v, ff[1], fma(E.w, ff[2], 0.5 * E.q * ff[3]))));
+}
+
+// One tracer on one face: c[6] are its stencil values, up[j] = u_j + alpha (j=0..4 used),
+// um[j] = u_j - alpha (j=1..5 used).  (utilities.cpp:376-377,388,395,431,439,473)
+EB_HD double tracer_face(const double c[6], const double up[6], const double um[6])
+{
+  const double fp = weno5(up[0] * c[0], up[1] * c[1], up[2] * c[2], up[3] * c[3], up[4] * c[4]);
+  const double fm = weno5(um[5] * c[5], um[4] * c[4], um[3] * c[3], um[2] * c[2], um[1] * c[1]);
+  return 0.5 * (fp + fm);
+}
+
+}  // namespace eb

@@ -1,0 +1,688 @@
+// ---------------------------------------------------------------------------
+// eulerb200.cu -- implementation of the C ABI in include/eulerb200.h (sm_100a).
+//
+// Kernels in this translation unit:
+//   rhs_fused_kernel     (rhs_kernel.cuh)  fEuler: faces + divergence, one pass
+//   pack_face_kernel     halo pack of EulerData::ExchangeStart (euler3D.hpp:644-786)
+//   ghost_face_kernel    materialise a face's ghost layers in the reference's
+//                        receive-buffer layout (euler3D.hpp:797-1166; tests, drop-in)
+//   wavespeed_kernel     local part of stability (utilities.cpp:505-513)
+// There is deliberately no host implementation of any of them.
+// ---------------------------------------------------------------------------
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#define EB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#include "host_setup.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------- NCCL, resolved at run time -------------------------------
+// (single-GPU use needs no NCCL at all; in a process that already loaded a libnccl.so.2,
+// e.g. PyTorch's bundled one, dlopen returns that same library)
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+#define EB_SYM(field, sym) *(void**)(&api.field) = dlsym(api.handle, sym); if (!api.field) return api
+  EB_SYM(GetUniqueId, "ncclGetUniqueId");
+  EB_SYM(CommInitRank, "ncclCommInitRank");
+  EB_SYM(CommDestroy, "ncclCommDestroy");
+  EB_SYM(Send, "ncclSend");
+  EB_SYM(Recv, "ncclRecv");
+  EB_SYM(AllReduce, "ncclAllReduce");
+  EB_SYM(GroupStart, "ncclGroupStart");
+  EB_SYM(GroupEnd, "ncclGroupEnd");
+  EB_SYM(GetErrorString, "ncclGetErrorString");
+#undef EB_SYM
+  api.ok = true;
+  return api;
+}
+
+// ----------------------------------- small kernels -----------------------------------
+
+struct FaceGeom {
+  long nx, ny, nz;
+  int nchem, f;
+  const double* w[6];
+};
+
+__device__ __forceinline__ void face_decode(const FaceGeom& g, long e, int& d, long& a, long& b, long& na)
+{
+  const int dir = g.f / 2;
+  na = (dir == 0) ? g.ny : g.nx;
+  d = (int)(e % 3);
+  const long r = e / 3;
+  a = r % na;
+  b = r / na;
+}
+__device__ __forceinline__ long face_cell(const FaceGeom& g, long src, long a, long b)
+{
+  const int dir = g.f / 2;
+  const long i = (dir == 0) ? src : a;
+  const long j = (dir == 0) ? a : (dir == 1 ? src : b);
+  const long k = (dir == 2) ? src : b;
+  return i + g.nx * (j + g.ny * k);
+}
+
+// What this rank sends through face f: its three layers nearest that face in increasing
+// index order, all NVAR values of a cell contiguous (euler3D.hpp:644-786).
+__global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
+{
+  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (e >= nent) return;
+  int d; long a, b, na;
+  face_decode(g, e, d, a, b, na);
+  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
+  const long src = (g.f % 2 == 0) ? d : n - 3 + d;
+  const long cell = face_cell(g, src, a, b);
+  const int nv = 5 + g.nchem;
+  double* o = buf + (long)nv * e;
+#pragma unroll
+  for (int v = 0; v < 5; v++) o[v] = g.w[v][cell];
+  for (int v = 0; v < g.nchem; v++) o[5 + v] = g.w[5][cell * g.nchem + v];
+}
+
+// Ghost layers of face f in the reference's receive-buffer layout, from the descriptor
+// the RHS kernel itself uses (so tests of this buffer test the kernel's ghost semantics).
+__global__ void ghost_face_kernel(const FaceGeom g, const eb::GhostFace G, double* __restrict__ dst, long nent)
+{
+  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (e >= nent) return;
+  const int nv = 5 + g.nchem;
+  double* o = dst + (long)nv * e;
+  if (G.mode == eb::GHOST_BUF) {
+    for (int v = 0; v < nv; v++) o[v] = G.buf[(long)nv * e + v];
+    return;
+  }
+  int d; long a, b, na;
+  face_decode(g, e, d, a, b, na);
+  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
+  const long pos = (g.f % 2 == 0) ? (long)d - 3 : n + d;
+  const long cell = face_cell(g, G.a + (long)G.b * pos, a, b);
+  for (int v = 0; v < 5; v++) {
+    const double x = g.w[v][cell];
+    o[v] = ((G.neg >> v) & 1u) ? -x : x;
+  }
+  for (int v = 0; v < g.nchem; v++) {
+    const double x = g.w[5][cell * g.nchem + v];
+    o[5 + v] = ((G.neg >> 5) & 1u) ? -x : x;
+  }
+}
+
+// utilities.cpp:505-513: alpha = max | |mx/rho| + sqrt(gamma p / rho) |  (my, mz only via p).
+// Warp-shuffle then one atomic per CTA; non-negative doubles order like their bit patterns.
+__global__ void wavespeed_kernel(const double* __restrict__ rho, const double* __restrict__ mx,
+                                 const double* __restrict__ my, const double* __restrict__ mz,
+                                 const double* __restrict__ et, long N, double gamma,
+                                 unsigned long long* __restrict__ out)
+{
+  double alpha = 0.0;
+  for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < N; c += (long)gridDim.x * blockDim.x) {
+    const double r = rho[c], a = mx[c], b = my[c], d = mz[c];
+    const double u = fabs(a / r);
+    const double p = (gamma - 1.0) * (et[c] - (a * a + b * b + d * d) * 0.5 / r);
+    const double x = fabs(u + eb::sun_sqrt(gamma * p / r));
+    alpha = (alpha < x) ? x : alpha;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double y = __shfl_xor_sync(0xffffffffu, alpha, o);
+    alpha = (alpha < y) ? y : alpha;
+  }
+  __shared__ double part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) part[wid] = alpha;
+  __syncthreads();
+  if (wid == 0) {
+    alpha = (lane < (blockDim.x >> 5)) ? part[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, alpha, o);
+      alpha = (alpha < y) ? y : alpha;
+    }
+    if (lane == 0) atomicMax(out, (unsigned long long)__double_as_longlong(alpha));
+  }
+}
+
+// DFMA throughput micro-benchmark: 8 independent dependency chains per thread.  Used by
+// bench.py for the FP64-pipe roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b)
+{
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 12345.678) out[0] = r;   // never true; keeps the chains alive
+}
+
+}  // namespace
+
+// ------------------------------------- context -------------------------------------
+
+struct eulerb200_ctx {
+  eulerb200_config cfg;
+  int device = 0;
+  std::string error;
+  int64_t launches = 0;
+
+  int* d_flag = nullptr;
+  int* h_flag = nullptr;                 // pinned
+  unsigned long long* d_alpha = nullptr;
+  double* h_alpha = nullptr;             // pinned
+
+  bool remote[6] = {false, false, false, false, false, false};
+  bool any_remote = false;
+  double* send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
+  bool exchange_open = false;
+
+  // staging for eulerb200_rhs_host (allocated on first use)
+  double* stage_w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* stage_wdot[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
+  static const int kMaxSlabs = 16;
+  cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
+  bool host_ready = false;
+  size_t max_smem_set = 0;
+};
+
+namespace {
+
+int fail(eulerb200_ctx* c, int code, const std::string& msg)
+{
+  if (c) c->error = msg; else g_create_error = msg;
+  return code;
+}
+#define EB_CUDA(c, call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(c, -2, std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #call); \
+  } while (0)
+#define EB_NCCL(c, call)                                                                  \
+  do {                                                                                    \
+    ncclResult_t r_ = (call);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      return fail(c, -3, std::string("NCCL error: ") + nccl().GetErrorString(r_) + " in " #call); \
+  } while (0)
+
+eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* const* wdot)
+{
+  const eulerb200_config& g = c->cfg;
+  eb::RhsParams P;
+  P.nx = g.nxl; P.ny = g.nyl; P.nz = g.nzl;
+  P.nchem = g.nchem;
+  P.gamma = g.gamma;
+  P.rdx = 1.0 / g.dx; P.rdy = 1.0 / g.dy; P.rdz = 1.0 / g.dz;
+  for (int f = 0; f < 5; f++) P.forcing[f] = g.forcing[f];
+  for (int f = 0; f < 6; f++) {
+    P.w[f] = (f < 5 || g.nchem > 0) ? w[f] : nullptr;
+    P.wdot[f] = (f < 5 || g.nchem > 0) ? wdot[f] : nullptr;
+    eb::ghost_face(g, f, c->recv[f], &P.ghost[f]);
+  }
+  P.state_flag = c->d_flag;
+  P.lo[0] = P.lo[1] = P.lo[2] = 0;
+  P.hi[0] = P.nx; P.hi[1] = P.ny; P.hi[2] = P.nz;
+  P.seg_len = 1;
+  return P;
+}
+
+// Evaluate the cells of [lo,hi) (clipped to non-empty) on `s`.
+int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long hi[3], cudaStream_t s)
+{
+  for (int d = 0; d < 3; d++) {
+    if (hi[d] <= lo[d]) return 0;
+    P.lo[d] = lo[d]; P.hi[d] = hi[d];
+  }
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem);
+  P.seg_len = L.seg_len;
+  if (L.smem > c->max_smem_set) {
+    EB_CUDA(c, cudaFuncSetAttribute(eb::rhs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    c->max_smem_set = L.smem;
+  }
+  eb::rhs_fused_kernel<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+FaceGeom face_geom(const eulerb200_ctx* c, int f, const double* const* w)
+{
+  FaceGeom g;
+  g.nx = c->cfg.nxl; g.ny = c->cfg.nyl; g.nz = c->cfg.nzl;
+  g.nchem = c->cfg.nchem; g.f = f;
+  for (int q = 0; q < 6; q++) g.w[q] = (q < 5 || c->cfg.nchem > 0) ? w[q] : nullptr;
+  return g;
+}
+
+int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
+{
+  if (!c->any_remote) return 0;
+  if (!c->comm) return fail(c, -3, "context has remote neighbours but eulerb200_comm_attach was not called");
+  const int nv = 5 + c->cfg.nchem;
+  for (int f = 0; f < 6; f++) {
+    if (!c->remote[f]) continue;
+    const long nent = eb::face_len(c->cfg, f) / nv;
+    pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), c->send[f], nent);
+    c->launches++;
+  }
+  EB_CUDA(c, cudaGetLastError());
+  EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
+  EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+  // Sends in face order W,E,S,N,B,F; receives in the order of the opposite faces, so that
+  // between any pair of ranks the k-th send meets the k-th receive (the job the tags do
+  // in euler3D.hpp:608-640,663-784).
+  EB_NCCL(c, nccl().GroupStart());
+  for (int f = 0; f < 6; f++) {
+    if (c->remote[f])
+      EB_NCCL(c, nccl().Send(c->send[f], (size_t)eb::face_len(c->cfg, f), ncclDouble, c->cfg.nbr[f], c->comm, c->comm_stream));
+    const int r = f ^ 1;
+    if (c->remote[r])
+      EB_NCCL(c, nccl().Recv(c->recv[r], (size_t)eb::face_len(c->cfg, r), ncclDouble, c->cfg.nbr[r], c->comm, c->comm_stream));
+  }
+  EB_NCCL(c, nccl().GroupEnd());
+  EB_CUDA(c, cudaEventRecord(c->ev_recv, c->comm_stream));
+  c->exchange_open = true;
+  return 0;
+}
+
+int exchange_end(eulerb200_ctx* c, cudaStream_t s)
+{
+  if (!c->exchange_open) return 0;
+  EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_recv, 0));
+  c->exchange_open = false;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------- C ABI -------------------------------------
+
+extern "C" {
+
+int eulerb200_version(void) { return EULERB200_VERSION; }
+
+int eulerb200_decompose(int32_t nprocs, int32_t rank, const int64_t* n, const int32_t* bc,
+                        int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr)
+{
+  return eb::decompose(nprocs, rank, n, bc, dims, coords, ext, nbr);
+}
+
+const char* eulerb200_last_error(const eulerb200_ctx* ctx)
+{
+  return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
+{
+  if (!cfg || !out) return fail(nullptr, -1, "null argument");
+  *out = nullptr;
+  if (cfg->nxl < 3 || cfg->nyl < 3 || cfg->nzl < 3) return fail(nullptr, -1, "local extents must be >= 3 (euler3D.hpp:483-494)");
+  if (cfg->nchem < 0 || 5 + cfg->nchem > 64) return fail(nullptr, -1, "nchem out of range");
+  if (!(cfg->dx > 0) || !(cfg->dy > 0) || !(cfg->dz > 0)) return fail(nullptr, -1, "mesh spacing must be positive");
+  for (int f = 0; f < 6; f++) {
+    eb::GhostFace g;
+    if (eb::ghost_face(*cfg, f, nullptr, &g) != 0)
+      return fail(nullptr, -1, "periodic face without a neighbour (set nbr[f] = rank for a wrap onto this rank)");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, -2, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  eulerb200_ctx* c = new eulerb200_ctx();
+  c->cfg = *cfg;
+  if (cfg->device >= 0) {
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
+  }
+  cudaGetDevice(&c->device);
+#define EB_CREATE(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      std::string m_ = std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #call; \
+      eulerb200_destroy(c);                                                               \
+      return fail(nullptr, -2, m_);                                                       \
+    }                                                                                     \
+  } while (0)
+  EB_CREATE(cudaMalloc(&c->d_flag, sizeof(int)));
+  EB_CREATE(cudaMemset(c->d_flag, 0, sizeof(int)));
+  EB_CREATE(cudaMallocHost(&c->h_flag, sizeof(int)));
+  EB_CREATE(cudaMalloc(&c->d_alpha, sizeof(unsigned long long)));
+  EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
+  for (int f = 0; f < 6; f++) {
+    c->remote[f] = eb::face_is_remote(*cfg, f);
+    if (c->remote[f]) {
+      c->any_remote = true;
+      EB_CREATE(cudaMalloc(&c->send[f], sizeof(double) * eb::face_len(*cfg, f)));
+      EB_CREATE(cudaMalloc(&c->recv[f], sizeof(double) * eb::face_len(*cfg, f)));
+    }
+  }
+  if (c->any_remote) {
+    EB_CREATE(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    EB_CREATE(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    EB_CREATE(cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
+  }
+#undef EB_CREATE
+  *out = c;
+  return 0;
+}
+
+int eulerb200_destroy(eulerb200_ctx* c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  for (int f = 0; f < 6; f++) {
+    if (c->send[f]) cudaFree(c->send[f]);
+    if (c->recv[f]) cudaFree(c->recv[f]);
+    if (c->stage_w[f]) cudaFree(c->stage_w[f]);
+    if (c->stage_wdot[f]) cudaFree(c->stage_wdot[f]);
+  }
+  if (c->host_ready) {
+    for (int s = 0; s < eulerb200_ctx::kMaxSlabs; s++) { cudaEventDestroy(c->ev_up[s]); cudaEventDestroy(c->ev_done[s]); }
+    cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_cmp); cudaStreamDestroy(c->s_d2h);
+  }
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+  if (c->ev_recv) cudaEventDestroy(c->ev_recv);
+  if (c->d_flag) cudaFree(c->d_flag);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->d_alpha) cudaFree(c->d_alpha);
+  if (c->h_alpha) cudaFreeHost(c->h_alpha);
+  delete c;
+  return 0;
+}
+
+int eulerb200_comm_unique_id(void* id_bytes)
+{
+  if (!nccl().ok) return fail(nullptr, -3, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  ncclResult_t r = nccl().GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, -3, std::string("ncclGetUniqueId: ") + nccl().GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == EULERB200_UNIQUE_ID_BYTES, "unique id size");
+  memcpy(id_bytes, &id, sizeof id);
+  return 0;
+}
+
+int eulerb200_comm_attach(eulerb200_ctx* c, const void* id_bytes)
+{
+  if (!c) return -1;
+  if (!nccl().ok) return fail(c, -3, "libnccl.so.2 could not be loaded");
+  EB_CUDA(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof id);
+  EB_NCCL(c, nccl().CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank));
+  return 0;
+}
+
+int eulerb200_exchange_start(eulerb200_ctx* c, const double* const* w, void* stream)
+{
+  if (!c || !w) return -1;
+  return exchange_start(c, w, (cudaStream_t)stream);
+}
+
+int eulerb200_exchange_end(eulerb200_ctx* c, void* stream)
+{
+  if (!c) return -1;
+  return exchange_end(c, (cudaStream_t)stream);
+}
+
+int64_t eulerb200_face_len(const eulerb200_ctx* c, int32_t face)
+{
+  return (c && face >= 0 && face < 6) ? eb::face_len(c->cfg, face) : -1;
+}
+
+int eulerb200_ghost_face(eulerb200_ctx* c, const double* const* w, int32_t f, double* dst, void* stream)
+{
+  if (!c || !w || !dst || f < 0 || f >= 6) return -1;
+  eb::GhostFace G;
+  eb::ghost_face(c->cfg, f, c->recv[f], &G);
+  const long nent = eb::face_len(c->cfg, f) / (5 + c->cfg.nchem);
+  ghost_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, (cudaStream_t)stream>>>(face_geom(c, f, w), G, dst, nent);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int eulerb200_rhs_async(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* stream)
+{
+  (void)t;   // every shipped forcing is time independent
+  if (!c || !w || !wdot) return -1;
+  for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++)
+    if (!w[f] || !wdot[f]) return fail(c, -1, "NULL sub-vector pointer (utilities.cpp:31-58)");
+  cudaStream_t s = (cudaStream_t)stream;
+  EB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), s));
+  const eb::RhsParams P = make_params(c, w, wdot);
+  const long n[3] = {P.nx, P.ny, P.nz};
+  if (!c->any_remote) {
+    const long lo[3] = {0, 0, 0};
+    return launch_box(c, P, lo, n, s);
+  }
+  // Overlap (the structure of utilities.cpp:61 -> 76-116 -> 119 -> 123-195): start the
+  // exchange, evaluate every cell whose stencils stay clear of the remote faces, wait for
+  // the halos, then evaluate the remaining shell as non-overlapping slabs.
+  int rc = exchange_start(c, w, s);
+  if (rc) return rc;
+  long lo[3], hi[3];
+  bool interior = true;
+  for (int d = 0; d < 3; d++) {
+    lo[d] = c->remote[2 * d] ? 3 : 0;
+    hi[d] = n[d] - (c->remote[2 * d + 1] ? 3 : 0);
+    if (hi[d] <= lo[d]) interior = false;
+  }
+  if (!interior) {
+    rc = exchange_end(c, s);
+    if (rc) return rc;
+    const long z[3] = {0, 0, 0};
+    return launch_box(c, P, z, n, s);
+  }
+  rc = launch_box(c, P, lo, hi, s);
+  if (rc) return rc;
+  rc = exchange_end(c, s);
+  if (rc) return rc;
+  {
+    const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low
+    const long b0[3] = {0, 0, hi[2]}, b1[3] = {n[0], n[1], n[2]};                 // z-high
+    const long c0[3] = {0, 0, lo[2]}, c1[3] = {n[0], lo[1], hi[2]};               // y-low
+    const long d0[3] = {0, hi[1], lo[2]}, d1[3] = {n[0], n[1], hi[2]};            // y-high
+    const long e0[3] = {0, lo[1], lo[2]}, e1[3] = {lo[0], hi[1], hi[2]};          // x-low
+    const long f0[3] = {hi[0], lo[1], lo[2]}, f1[3] = {n[0], hi[1], hi[2]};       // x-high
+    if ((rc = launch_box(c, P, a0, a1, s))) return rc;
+    if ((rc = launch_box(c, P, b0, b1, s))) return rc;
+    if ((rc = launch_box(c, P, c0, c1, s))) return rc;
+    if ((rc = launch_box(c, P, d0, d1, s))) return rc;
+    if ((rc = launch_box(c, P, e0, e1, s))) return rc;
+    if ((rc = launch_box(c, P, f0, f1, s))) return rc;
+  }
+  return 0;
+}
+
+int eulerb200_state_flag(eulerb200_ctx* c, void* stream, int32_t* bits)
+{
+  if (!c || !bits) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  EB_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  EB_CUDA(c, cudaStreamSynchronize(s));
+  *bits = *c->h_flag;
+  return 0;
+}
+
+int eulerb200_rhs(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* stream)
+{
+  int rc = eulerb200_rhs_async(c, t, w, wdot, stream);
+  if (rc) return rc;
+  int32_t bits = 0;
+  rc = eulerb200_state_flag(c, stream, &bits);
+  if (rc) return rc;
+  if (bits) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
+    return fail(c, -1, msg);
+  }
+  return 0;
+}
+
+int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, double* const* wdh)
+{
+  if (!c || !wh || !wdh) return -1;
+  const eulerb200_config& g = c->cfg;
+  const long plane = g.nxl * g.nyl, N = plane * g.nzl;
+  const int nsub = 5 + (g.nchem > 0 ? 1 : 0);
+  EB_CUDA(c, cudaSetDevice(c->device));
+  if (!c->host_ready) {
+    for (int f = 0; f < nsub; f++) {
+      const size_t bytes = sizeof(double) * N * (f < 5 ? 1 : g.nchem);
+      EB_CUDA(c, cudaMalloc(&c->stage_w[f], bytes));
+      EB_CUDA(c, cudaMalloc(&c->stage_wdot[f], bytes));
+    }
+    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int s = 0; s < eulerb200_ctx::kMaxSlabs; s++) {
+      EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_up[s], cudaEventDisableTiming));
+      EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
+    }
+    c->host_ready = true;
+  }
+  if (c->any_remote) {
+    // with remote neighbours the halo exchange needs the whole state: no slab pipeline
+    for (int f = 0; f < nsub; f++)
+      EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f], wh[f], sizeof(double) * N * (f < 5 ? 1 : g.nchem), cudaMemcpyHostToDevice, c->s_cmp));
+    int rc = eulerb200_rhs_async(c, t, c->stage_w, c->stage_wdot, c->s_cmp);
+    if (rc) return rc;
+    for (int f = 0; f < nsub; f++)
+      EB_CUDA(c, cudaMemcpyAsync(wdh[f], c->stage_wdot[f], sizeof(double) * N * (f < 5 ? 1 : g.nchem), cudaMemcpyDeviceToHost, c->s_cmp));
+  } else {
+    // z-slab pipeline: upload slab s+1 while slab s is evaluated and slab s-1 is downloaded.
+    // A slab can be evaluated once the slab above it is resident (3-plane stencil reach);
+    // with a periodic wrap in z the first slab also needs the last one, so it goes last.
+    int S = (int)std::min<long>(eulerb200_ctx::kMaxSlabs, std::max<long>(1, g.nzl / 8));
+    long zb[eulerb200_ctx::kMaxSlabs + 1];
+    for (int s = 0; s <= S; s++) zb[s] = g.nzl * s / S;
+    EB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_cmp));
+    for (int s = 0; s < S; s++) {
+      for (int f = 0; f < nsub; f++) {
+        const long m = (f < 5 ? 1 : g.nchem);
+        EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f] + zb[s] * plane * m, wh[f] + zb[s] * plane * m,
+                                   sizeof(double) * (zb[s + 1] - zb[s]) * plane * m, cudaMemcpyHostToDevice, c->s_h2d));
+      }
+      EB_CUDA(c, cudaEventRecord(c->ev_up[s], c->s_h2d));
+    }
+    const bool wrap = (g.nbr[4] == g.rank);
+    const eb::RhsParams P = make_params(c, c->stage_w, c->stage_wdot);
+    for (int q = 0; q < S; q++) {
+      const int s = wrap ? (q + 1) % S : q;
+      const int need = (wrap && s == 0) ? S - 1 : std::min(s + 1, S - 1);
+      EB_CUDA(c, cudaStreamWaitEvent(c->s_cmp, c->ev_up[need], 0));
+      const long lo[3] = {0, 0, zb[s]}, hi[3] = {g.nxl, g.nyl, zb[s + 1]};
+      int rc = launch_box(c, P, lo, hi, c->s_cmp);
+      if (rc) return rc;
+      EB_CUDA(c, cudaEventRecord(c->ev_done[s], c->s_cmp));
+      EB_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_done[s], 0));
+      for (int f = 0; f < nsub; f++) {
+        const long m = (f < 5 ? 1 : g.nchem);
+        EB_CUDA(c, cudaMemcpyAsync(wdh[f] + zb[s] * plane * m, c->stage_wdot[f] + zb[s] * plane * m,
+                                   sizeof(double) * (zb[s + 1] - zb[s]) * plane * m, cudaMemcpyDeviceToHost, c->s_d2h));
+      }
+    }
+    EB_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+  }
+  int32_t bits = 0;
+  int rc = eulerb200_state_flag(c, c->s_cmp, &bits);
+  if (rc) return rc;
+  if (bits) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
+    return fail(c, -1, msg);
+  }
+  return 0;
+}
+
+int eulerb200_stability(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void* stream)
+{
+  if (!c || !w || !dt_stab) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
+  EB_CUDA(c, cudaMemsetAsync(c->d_alpha, 0, sizeof(unsigned long long), s));
+  const unsigned blocks = (unsigned)std::min<long>((N + 255) / 256, 148L * 8);
+  wavespeed_kernel<<<blocks, 256, 0, s>>>(w[0], w[1], w[2], w[3], w[4], N, c->cfg.gamma, c->d_alpha);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  if (c->cfg.nranks > 1 && c->comm)   // utilities.cpp:516
+    EB_NCCL(c, nccl().AllReduce(c->d_alpha, c->d_alpha, 1, ncclDouble, ncclMax, c->comm, s));
+  EB_CUDA(c, cudaMemcpyAsync(c->h_alpha, c->d_alpha, sizeof(double), cudaMemcpyDeviceToHost, s));
+  EB_CUDA(c, cudaStreamSynchronize(s));
+  const double h = std::min(std::min(c->cfg.dx, c->cfg.dy), c->cfg.dz);
+  *dt_stab = cfl * h / *c->h_alpha;   // utilities.cpp:520
+  return 0;
+}
+
+int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
+
+int eulerb200_fp64_peak(double* tflops)
+{
+  if (!tflops) return -1;
+  double* d = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&d, sizeof(double)) != cudaSuccess) return fail(nullptr, -2, "cudaMalloc failed");
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256, iters = 20000;
+  dfma_peak_kernel<<<blocks, threads>>>(d, 2000, 0.999999, 1e-9);   // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return fail(nullptr, -2, "dfma kernel failed"); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

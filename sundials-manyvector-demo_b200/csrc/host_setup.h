@@ -1,0 +1,150 @@
+// ---------------------------------------------------------------------------
+// host_setup.h -- host-side arithmetic behind the C ABI: domain decomposition,
+// ghost-face descriptors, launch geometry.  No CUDA calls in here (the CPU logic tests
+// include it too).
+// ---------------------------------------------------------------------------
+#pragma once
+#include <stdint.h>
+#include <algorithm>
+#include <vector>
+#include "../../include/eulerb200.h"
+#include "rhs_kernel.cuh"
+
+namespace eb {
+
+// MPI_Dims_create as every mainstream MPI answers it: a balanced factorisation in
+// non-increasing order (used by EulerData::SetupDecomp, euler3D.hpp:430).
+inline void dims_create(int nnodes, int ndims, int* dims)
+{
+  std::vector<int> primes;
+  int n = nnodes;
+  for (int p = 2; p * p <= n; p++)
+    while (n % p == 0) { primes.push_back(p); n /= p; }
+  if (n > 1) primes.push_back(n);
+  std::sort(primes.begin(), primes.end(), [](int a, int b) { return a > b; });
+  std::vector<int> bins(ndims, 1);
+  for (size_t q = 0; q < primes.size() && ndims > 0; q++) {
+    int best = 0;
+    for (int d = 1; d < ndims; d++)
+      if (bins[d] < bins[best]) best = d;
+    bins[best] *= primes[q];
+  }
+  std::sort(bins.begin(), bins.end(), [](int a, int b) { return a > b; });
+  for (int d = 0; d < ndims; d++) dims[d] = bins[d];
+}
+
+// euler3D.hpp:416-440,443-457,466-494,505-567
+inline int decompose(int nprocs, int rank, const int64_t* n, const int32_t* bc,
+                     int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr)
+{
+  for (int d = 0; d < 3; d++)
+    if ((bc[2 * d] == EULERB200_BC_PERIODIC) != (bc[2 * d + 1] == EULERB200_BC_PERIODIC)) return 1;
+  int truedims = 0;
+  for (int d = 0; d < 3; d++) truedims += (n[d] > 3) ? 1 : 0;
+  int sugg[3] = {1, 1, 1};
+  dims_create(nprocs, truedims, sugg);
+  int q = 0;
+  for (int d = 0; d < 3; d++) dims[d] = (n[d] > 3) ? sugg[q++] : 1;
+  if (dims[0] * dims[1] * dims[2] != nprocs) return -1;   // e.g. nprocs > 1 on a 3x3x3 grid
+  // non-reordered Cartesian communicator: row-major ranks, coords[0] slowest
+  int r = rank;
+  coords[2] = r % dims[2]; r /= dims[2];
+  coords[1] = r % dims[1]; r /= dims[1];
+  coords[0] = r;
+  for (int d = 0; d < 3; d++) {
+    ext[2 * d] = n[d] * coords[d] / dims[d];
+    ext[2 * d + 1] = n[d] * (coords[d] + 1) / dims[d] - 1;
+    if (ext[2 * d + 1] - ext[2 * d] + 1 < 3) return -1;
+  }
+  for (int d = 0; d < 3; d++)
+    for (int side = 0; side < 2; side++) {
+      const bool periodic = bc[2 * d] == EULERB200_BC_PERIODIC;
+      const bool inner = side == 0 ? coords[d] > 0 : coords[d] < dims[d] - 1;
+      int v = EULERB200_NO_NEIGHBOR;
+      if (inner || periodic) {
+        int c[3] = {coords[0], coords[1], coords[2]};
+        c[d] = (c[d] + (side == 0 ? -1 : 1) + dims[d]) % dims[d];
+        v = (c[0] * dims[1] + c[1]) * dims[2] + c[2];
+      }
+      nbr[2 * d + side] = v;
+    }
+  return 0;
+}
+
+inline int64_t face_len(const eulerb200_config& c, int f)
+{
+  const int64_t nv = 5 + c.nchem;
+  if (f < 2) return nv * 3 * c.nyl * c.nzl;
+  if (f < 4) return nv * 3 * c.nxl * c.nzl;
+  return nv * 3 * c.nxl * c.nyl;
+}
+
+inline bool face_is_remote(const eulerb200_config& c, int f)
+{
+  return c.nbr[f] != EULERB200_NO_NEIGHBOR && c.nbr[f] != c.rank;
+}
+
+// Ghost descriptor of face f.  Physical boundaries (euler3D.hpp:797-1166): low side
+// mirrors (ghost -1-m <- own m), high side COPIES (ghost n+m <- own n-3+m); reflecting
+// negates the face-normal momentum, Dirichlet everything.  A periodic wrap onto the same
+// rank is an index shift by n.  Anything else reads the halo buffer `recv`.
+inline int ghost_face(const eulerb200_config& c, int f, const double* recv, GhostFace* g)
+{
+  const int dir = f / 2, side = f % 2;
+  const long n = dir == 0 ? c.nxl : (dir == 1 ? c.nyl : c.nzl);
+  g->buf = nullptr;
+  g->neg = 0u;
+  if (c.nbr[f] == EULERB200_NO_NEIGHBOR) {
+    g->mode = GHOST_MAP;
+    if (side == 0) { g->a = -1; g->b = -1; } else { g->a = -3; g->b = 1; }
+    switch (c.bc[f]) {
+      case EULERB200_BC_NEUMANN: break;
+      case EULERB200_BC_REFLECTING: g->neg = 1u << (1 + dir); break;
+      case EULERB200_BC_DIRICHLET: g->neg = 0x3Fu; break;
+      default: return -1;   // a periodic face always has a neighbour (possibly this rank)
+    }
+  } else if (c.nbr[f] == c.rank) {
+    g->mode = GHOST_MAP;
+    g->b = 1;
+    g->a = side == 0 ? n : -n;
+  } else {
+    g->mode = GHOST_BUF;
+    g->a = 0; g->b = 0;
+    g->buf = recv;
+  }
+  return 0;
+}
+
+struct LaunchGeom {
+  unsigned gx, gy, gz;
+  int tx, ty;
+  int seg_len;
+  size_t smem;
+};
+
+// Tile shape: 256 threads; a full warp along x whenever the box is at least 31 cells
+// wide, otherwise the narrowest power of two that holds extent+1 faces (thin boxes such
+// as the 3-cell-wide hurricane plane then put the threads along y).
+inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256)
+{
+  LaunchGeom L;
+  const long ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  int tx = 32;
+  while (tx > 2 && tx / 2 >= ex + 1) tx /= 2;
+  int ty = threads / tx;
+  while (ty > 2 && ty / 2 >= ey + 1) ty /= 2;
+  L.tx = tx; L.ty = ty;
+  L.gx = (unsigned)((ex + tx - 2) / (tx - 1));
+  L.gy = (unsigned)((ey + ty - 2) / (ty - 1));
+  // z-segments: enough CTAs for ~20 waves on 148 SMs x 2 resident CTAs, but at least 8
+  // cells per segment (one extra z-face is computed per segment)
+  const long tiles = (long)L.gx * L.gy;
+  long nseg = (5920 + tiles - 1) / tiles;
+  nseg = std::max(1L, std::min(nseg, (ez + 7) / 8));
+  L.seg_len = (int)((ez + nseg - 1) / nseg);
+  L.gz = (unsigned)((ez + L.seg_len - 1) / L.seg_len);
+  L.smem = (size_t)3 * (5 + nchem) * tx * ty * sizeof(double);
+  return L;
+}
+
+}  // namespace eb

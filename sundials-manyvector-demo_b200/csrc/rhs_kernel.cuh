@@ -1,0 +1,249 @@
+// ---------------------------------------------------------------------------
+// rhs_kernel.cuh -- the fused fluid right-hand side kernel (sm_100a).
+//
+// One launch evaluates  wdot = G - div F(w)  for every owned cell: what the reference
+// does in five passes over memory (zero wdot, forcing, interior faces, boundary faces,
+// divergence: /root/reference/src/utilities.cpp:28,65,76-116,123-195,198-245) with three
+// flux scratch arrays (euler3D.hpp:497-499) is done here in a single pass that reads the
+// state once and writes wdot once; face fluxes only ever exist in shared memory.
+//
+// Work decomposition (FP64-pipe bound, so the aim is: no redundant faces, no spills
+// of the carried state, everything else on the other pipes):
+//   * a CTA owns a (TX-1) x (TY-1) column of cells and marches along z over one
+//     z-segment; thread (tx,ty) computes the LOWER x- and y-face of its cell and the
+//     z-face above it.  The upper x/y faces come from the neighbouring threads through
+//     shared memory; the last thread column/row of the tile only supplies those faces.
+//   * the z-face below a cell is the one the same thread computed in the previous
+//     step (kept in a thread-private shared-memory slot), so along z nothing is
+//     computed twice except one face per segment.
+//   * stencil values are read straight from global memory through L1 (each value is
+//     reused by 6 faces x 3 directions; the FP64 pipe, not the LSU, is the limiter).
+//   * ghost cells are never materialised for physical boundaries: each of the six
+//     faces carries either an index map into the owned cells plus a sign mask
+//     (periodic wrap / mirror / copy, euler3D.hpp:797-1166) or a pointer to the halo
+//     buffer a neighbouring rank filled (reference wire layout, euler3D.hpp:648,696,744).
+//
+// Compiles under nvcc for the product and under g++ with tests/emu/cuda_emu.h for the
+// CPU-side logic tests (never shipped).
+// ---------------------------------------------------------------------------
+#pragma once
+#include "euler_math.cuh"
+
+namespace eb {
+
+enum { GHOST_MAP = 0, GHOST_BUF = 1 };
+
+// How stencil positions beyond one side of the owned range along an axis are resolved.
+struct GhostFace {
+  int mode;            // GHOST_MAP: owned index = a + b*pos ; GHOST_BUF: halo buffer
+  int b;
+  long a;
+  unsigned neg;        // bit v (0..4 fluid field, 5 = all tracers): negate the value
+  const double* buf;   // GHOST_BUF: v + nv*(d + 3*(ta + na*tb)), d = layer 0..2
+};
+
+struct RhsParams {
+  long nx, ny, nz;          // owned extents (EulerData::nxl,nyl,nzl)
+  int nchem;
+  int seg_len;              // cells per z-segment
+  double gamma;
+  double rdx, rdy, rdz;     // 1/dx, 1/dy, 1/dz
+  double forcing[5];        // constant forcing assigned into wdot (external_forces hook)
+  const double* w[6];       // rho, mx, my, mz, et (SoA), chem (AoS, species fastest)
+  double* wdot[6];
+  GhostFace ghost[6];       // W,E,S,N,B,F
+  int* state_flag;          // OR of legal_state failure bits (euler3D.hpp:1405-1414)
+  // sub-box of cells to evaluate: [lo, hi) per axis (the whole box for a single launch;
+  // interior / boundary shells when the halo exchange is overlapped)
+  long lo[3], hi[3];
+};
+
+// One resolved stencil point: where to read it and which fields change sign.
+struct StencilPt {
+  long off;        // owned: cell index; halo buffer: index of field 0
+  unsigned neg;
+  int src;         // -1 owned, else face id of the halo buffer
+};
+
+// Resolve the six points pos = idx-3 .. idx+2 along `dir` for the face whose index along
+// that axis is idx (cell coordinates i,j,k hold idx in component dir).
+template <bool GEN>
+EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilPt pt[6])
+{
+  const long stride = (dir == 0) ? 1 : (dir == 1 ? P.nx : P.nx * P.ny);
+  const long idx = (dir == 0) ? i : (dir == 1 ? j : k);
+  const long cell = i + P.nx * (j + P.ny * k);   // may lie one past the end along dir
+#pragma unroll
+  for (int l = 0; l < 6; l++) {
+    const long pos = idx - 3 + l;
+    pt[l].off = cell + (l - 3) * stride;
+    pt[l].neg = 0u;
+    pt[l].src = -1;
+    if (GEN) {
+      const long n = (dir == 0) ? P.nx : (dir == 1 ? P.ny : P.nz);
+      if (pos < 0 || pos >= n) {
+        const int f = 2 * dir + (pos >= n ? 1 : 0);
+        const GhostFace& G = P.ghost[f];
+        if (G.mode == GHOST_MAP) {
+          const long mapped = G.a + (long)G.b * pos;
+          pt[l].off = cell + (mapped - idx) * stride;
+          pt[l].neg = G.neg;
+        } else {
+          const long d = (pos < 0) ? pos + 3 : pos - n;
+          const long ta = (dir == 0) ? j : i;
+          const long tb = (dir == 2) ? j : k;
+          const long na = (dir == 0) ? P.ny : P.nx;
+          pt[l].off = (long)(5 + P.nchem) * (d + 3 * (ta + na * tb));
+          pt[l].src = f;
+        }
+      }
+    }
+  }
+}
+
+template <bool GEN>
+EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
+{
+  if (GEN) {
+    double x = (pt.src < 0) ? P.w[field][pt.off] : P.ghost[pt.src].buf[pt.off + field];
+    return ((pt.neg >> field) & 1u) ? -x : x;
+  }
+  return P.w[field][pt.off];
+}
+
+template <bool GEN>
+EB_HD double load_chem(const RhsParams& P, const StencilPt& pt, int v)
+{
+  if (GEN) {
+    double x = (pt.src < 0) ? P.w[5][pt.off * P.nchem + v] : P.ghost[pt.src].buf[pt.off + 5 + v];
+    return ((pt.neg >> 5) & 1u) ? -x : x;
+  }
+  return P.w[5][pt.off * P.nchem + v];
+}
+
+// Face flux of all NVAR fields for the face below cell (i,j,k) along `dir`.  Each flux is
+// handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
+// tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
+// i.e. of cell (i,j,k) itself.
+template <bool GEN, class Emit>
+EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emit)
+{
+  StencilPt pt[6];
+  resolve<GEN>(P, dir, i, j, k, pt);
+
+  // sweep-aligned momentum order after the reference's swap (utilities.cpp:283-285)
+  const int fn = 1 + dir;
+  const int f1 = (dir == 1) ? 1 : 2;
+  const int f2 = (dir == 2) ? 1 : 3;
+
+  FluidStencil s;
+#pragma unroll
+  for (int l = 0; l < 6; l++) {
+    s.r[l] = load_fluid<GEN>(P, pt[l], 0);
+    s.mn[l] = load_fluid<GEN>(P, pt[l], fn);
+    s.m1[l] = load_fluid<GEN>(P, pt[l], f1);
+    s.m2[l] = load_fluid<GEN>(P, pt[l], f2);
+    s.e[l] = load_fluid<GEN>(P, pt[l], 4);
+  }
+
+  double f[5], alpha, u[6], p3;
+  fluid_face(s, P.gamma, f, alpha, u, p3);
+  const int bits = ((s.r[3] > 0.0) ? 0 : 1) | ((s.e[3] > 0.0) ? 0 : 2) | ((p3 > 0.0) ? 0 : 4);
+
+  emit(0, f[0]);
+  emit(fn, f[1]);
+  emit(f1, f[2]);
+  emit(f2, f[3]);
+  emit(4, f[4]);
+
+  if (P.nchem > 0) {
+    double up[6], um[6];
+#pragma unroll
+    for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
+#pragma unroll 1
+    for (int v = 0; v < P.nchem; v++) {
+      double c[6];
+#pragma unroll
+      for (int l = 0; l < 6; l++) c[l] = load_chem<GEN>(P, pt[l], v);
+      emit(5 + v, tracer_face(c, up, um));
+    }
+  }
+  return bits;
+}
+
+template <class Emit>
+EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, long k, Emit emit)
+{
+  return gen ? face_all<true>(P, dir, i, j, k, emit) : face_all<false>(P, dir, i, j, k, emit);
+}
+
+#if defined(__CUDACC__) || defined(EB_CUDA_EMU)
+
+// Dynamic shared memory: three arrays [NVAR][T] of doubles: FX, FY (exchanged with the
+// +x / +y neighbour thread) and ZLO (thread-private: flux through the z-face below).
+__global__ void rhs_fused_kernel(const RhsParams P)
+{
+  EB_DYN_SMEM(double, smem);
+  const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
+  const int nv = 5 + P.nchem;
+  double* FX = smem + t;
+  double* FY = smem + (long)nv * T + t;
+  double* ZLO = smem + 2L * nv * T + t;
+
+  const long ti0 = P.lo[0] + (long)blockIdx.x * (TX - 1);
+  const long tj0 = P.lo[1] + (long)blockIdx.y * (TY - 1);
+  const long i = ti0 + tx, j = tj0 + ty;
+  const long k0 = P.lo[2] + (long)blockIdx.z * P.seg_len;
+  const long k1 = (k0 + P.seg_len < P.hi[2]) ? k0 + P.seg_len : P.hi[2];
+
+  const bool row_ok = (ty < TY - 1) && (j < P.hi[1]);
+  const bool col_ok = (tx < TX - 1) && (i < P.hi[0]);
+  const bool owns = row_ok && col_ok;                 // this thread owns a cell column
+  const bool need_x = row_ok && (i <= P.hi[0]);       // lower x-face at position i
+  const bool need_y = col_ok && (j <= P.hi[1]);       // lower y-face at position j
+
+  // CTA-uniform: does any stencil of this tile reach beyond the owned range in x / y?
+  const bool gen_x = (ti0 - 3 < 0) || (ti0 + TX - 1 + 2 >= P.nx);
+  const bool gen_y = (tj0 - 3 < 0) || (tj0 + TY - 1 + 2 >= P.ny);
+
+  int mask = 0;
+
+  // z-face below the first plane of the segment
+  if (owns)
+    face_dispatch(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
+                  [&](int v, double x) { ZLO[v * T] = x; });
+
+  for (long k = k0; k < k1; k++) {
+    // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
+    if (need_x) {
+      const int bits = face_dispatch(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * T] = x; });
+      if (owns) mask |= bits;
+    }
+    if (need_y)
+      face_dispatch(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
+    __syncthreads();
+
+    // ---- phase B: z-face above cell (i,j,k); each flux closes the divergence of its
+    //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
+    if (owns) {
+      const long cell = i + P.nx * (j + P.ny * k);
+      face_dispatch(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
+                    [&](int v, double zup) {
+                      const double div = ((FX[v * T + 1] - FX[v * T]) * P.rdx
+                                        + (FY[v * T + TX] - FY[v * T]) * P.rdy)
+                                        + (zup - ZLO[v * T]) * P.rdz;
+                      ZLO[v * T] = zup;
+                      if (v < 5) P.wdot[v][cell] = P.forcing[v] - div;
+                      else P.wdot[5][cell * P.nchem + (v - 5)] = 0.0 - div;
+                    });
+    }
+    __syncthreads();
+  }
+
+  if (mask) atomicOr(P.state_flag, mask);
+}
+
+#endif  // __CUDACC__ || EB_CUDA_EMU
+
+}  // namespace eb

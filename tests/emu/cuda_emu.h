@@ -1,0 +1,111 @@
+// ---------------------------------------------------------------------------
+// cuda_emu.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE, never linked into the product.
+//
+// Just enough of the CUDA execution model to run the kernel SOURCE of
+// sundials-manyvector-demo_b200/csrc/rhs_kernel.cuh on the CPU in the "not gpu" test
+// tier, so that index arithmetic, ghost maps, shared-memory exchange and barrier
+// placement can be checked against the oracle in a container without a GPU.
+// It proves nothing about performance and is not a fallback: the product library
+// (libeulerb200.so) contains no host path and fails loudly without a device.
+//
+// Model: one CTA at a time; each CUDA thread is a ucontext fiber; __syncthreads()
+// yields to a round-robin scheduler that resumes the fibers once all of them have
+// arrived (or exited).  threadIdx/blockIdx/blockDim/gridDim are plain globals that
+// the scheduler rewrites on every switch.
+// ---------------------------------------------------------------------------
+#pragma once
+#include <ucontext.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define EB_CUDA_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct uint3_emu { unsigned x, y, z; };
+
+namespace cuda_emu {
+inline uint3_emu& tidx() { static uint3_emu v; return v; }
+inline uint3_emu& bidx() { static uint3_emu v; return v; }
+inline dim3& bdim() { static dim3 v; return v; }
+inline dim3& gdim() { static dim3 v; return v; }
+inline void*& shared_base() { static void* p = nullptr; return p; }
+
+struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done; uint3_emu tid; };
+inline std::vector<Fiber>& fibers() { static std::vector<Fiber> f; return f; }
+inline int& current() { static int c = -1; return c; }
+inline ucontext_t& sched_ctx() { static ucontext_t c; return c; }
+
+inline void yield_to_scheduler() { swapcontext(&fibers()[current()].ctx, &sched_ctx()); }
+
+template <class Kernel, class Params> struct Launch {
+  static Kernel kernel;
+  static const Params* params;
+  static void entry() { kernel(*params); fibers()[current()].done = true; swapcontext(&fibers()[current()].ctx, &sched_ctx()); }
+};
+template <class K, class P> K Launch<K, P>::kernel;
+template <class K, class P> const P* Launch<K, P>::params;
+
+// Run kernel(params) over grid x block with `shmem` bytes of dynamic shared memory.
+template <class Params>
+void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, const Params& params)
+{
+  typedef Launch<void (*)(const Params), Params> L;
+  L::kernel = kernel;
+  L::params = &params;
+  gdim() = grid; bdim() = block;
+  const int T = block.x * block.y * block.z;
+  std::vector<char> smem(shmem + 64);
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        bidx().x = bx; bidx().y = by; bidx().z = bz;
+        memset(smem.data(), 0xFF, smem.size());       // poison: NaNs if read before written
+        shared_base() = smem.data();
+        fibers().assign(T, Fiber());
+        for (int t = 0; t < T; t++) {
+          Fiber& f = fibers()[t];
+          f.stack.resize(256 * 1024);
+          f.done = false;
+          f.tid.x = t % block.x; f.tid.y = (t / block.x) % block.y; f.tid.z = t / (block.x * block.y);
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack.data();
+          f.ctx.uc_stack.ss_size = f.stack.size();
+          f.ctx.uc_link = &sched_ctx();
+          makecontext(&f.ctx, (void (*)())L::entry, 0);
+        }
+        // each pass resumes every live fiber once: from one barrier to the next
+        // (alternating the order between passes makes a missing barrier show up as wrong data)
+        bool any = true;
+        int pass = 0;
+        while (any) {
+          any = false;
+          pass++;
+          for (int q = 0; q < T; q++) {
+            const int t = (pass & 1) ? q : T - 1 - q;
+            if (fibers()[t].done) continue;
+            any = true;
+            current() = t;
+            tidx() = fibers()[t].tid;
+            swapcontext(&sched_ctx(), &fibers()[t].ctx);
+          }
+        }
+      }
+}
+}  // namespace cuda_emu
+
+#define threadIdx (cuda_emu::tidx())
+#define blockIdx (cuda_emu::bidx())
+#define blockDim (cuda_emu::bdim())
+#define gridDim (cuda_emu::gdim())
+#define EB_DYN_SMEM(type, name) type* name = (type*)cuda_emu::shared_base()
+
+inline void __syncthreads() { cuda_emu::yield_to_scheduler(); }
+inline int atomicOr(int* addr, int v) { int old = *addr; *addr = old | v; return old; }

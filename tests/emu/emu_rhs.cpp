@@ -1,0 +1,37 @@
+// ---------------------------------------------------------------------------
+// emu_rhs.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+// Runs the kernel source of the product (rhs_kernel.cuh) and its host-side set-up
+// (host_setup.h) on the CPU through tests/emu/cuda_emu.h, for the "not gpu" tests.
+// ---------------------------------------------------------------------------
+#include "cuda_emu.h"
+#include "../../sundials-manyvector-demo_b200/csrc/host_setup.h"
+
+extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
+                       const double* const* recv, int* state_bits, const long* lo, const long* hi,
+                       int threads)
+{
+  eb::RhsParams P;
+  P.nx = cfg->nxl; P.ny = cfg->nyl; P.nz = cfg->nzl;
+  P.nchem = cfg->nchem;
+  P.gamma = cfg->gamma;
+  P.rdx = 1.0 / cfg->dx; P.rdy = 1.0 / cfg->dy; P.rdz = 1.0 / cfg->dz;
+  for (int f = 0; f < 5; f++) P.forcing[f] = cfg->forcing[f];
+  for (int f = 0; f < 6; f++) { P.w[f] = w[f]; P.wdot[f] = wdot[f]; }
+  for (int f = 0; f < 6; f++)
+    if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
+  int flag = 0;
+  P.state_flag = &flag;
+  const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};
+  for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
+  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads);
+  P.seg_len = L.seg_len;
+  cuda_emu::launch(eb::rhs_fused_kernel, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+  *state_bits = flag;
+  return flag ? -1 : 0;
+}
+
+extern "C" int emu_decompose(int nprocs, int rank, const int64_t* n, const int32_t* bc,
+                             int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr)
+{
+  return eb::decompose(nprocs, rank, n, bc, dims, coords, ext, nbr);
+}
