@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -218,9 +219,27 @@ struct eulerb200_ctx {
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
   size_t max_smem_set = 0;
+  int variant = 0;
 };
 
 namespace {
+
+// Compiled variants of the RHS kernel: threads per CTA and resident CTAs per SM fix the
+// register budget (65536 / (threads * CTAs)).  EULERB200_VARIANT selects one by index for
+// tuning runs; the default is the fastest measured on B200 (profiles/).
+struct KernelVariant {
+  void (*fn)(const eb::RhsParams);
+  int threads;
+  const char* name;
+};
+const KernelVariant kVariants[] = {
+    {eb::rhs_fused_kernel<256, 1>, 256, "256x1 (<=255 regs)"},
+    {eb::rhs_fused_kernel<384, 1>, 384, "384x1 (<=168 regs)"},
+    {eb::rhs_fused_kernel<512, 1>, 512, "512x1 (<=128 regs)"},
+    {eb::rhs_fused_kernel<256, 2>, 256, "256x2 (<=128 regs)"},
+};
+const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+const int kDefaultVariant = 1;
 
 int fail(eulerb200_ctx* c, int code, const std::string& msg)
 {
@@ -268,13 +287,14 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     if (hi[d] <= lo[d]) return 0;
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem);
+  const KernelVariant& V = kVariants[c->variant];
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads);
   P.seg_len = L.seg_len;
   if (L.smem > c->max_smem_set) {
-    EB_CUDA(c, cudaFuncSetAttribute(eb::rhs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     c->max_smem_set = L.smem;
   }
-  eb::rhs_fused_kernel<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
+  V.fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
@@ -365,6 +385,11 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     return fail(nullptr, -2, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
   eulerb200_ctx* c = new eulerb200_ctx();
   c->cfg = *cfg;
+  c->variant = kDefaultVariant;
+  if (const char* ev = getenv("EULERB200_VARIANT")) {
+    const int v = atoi(ev);
+    if (v >= 0 && v < kNumVariants) c->variant = v;
+  }
   if (cfg->device >= 0) {
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }

@@ -111,16 +111,6 @@ EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
   return P.w[field][pt.off];
 }
 
-template <bool GEN>
-EB_HD double load_chem(const RhsParams& P, const StencilPt& pt, int v)
-{
-  if (GEN) {
-    double x = (pt.src < 0) ? P.w[5][pt.off * P.nchem + v] : P.ghost[pt.src].buf[pt.off + 5 + v];
-    return ((pt.neg >> 5) & 1u) ? -x : x;
-  }
-  return P.w[5][pt.off * P.nchem + v];
-}
-
 // Face flux of all NVAR fields for the face below cell (i,j,k) along `dir`.  Each flux is
 // handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
@@ -160,12 +150,56 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     double up[6], um[6];
 #pragma unroll
     for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
-#pragma unroll 1
-    for (int v = 0; v < P.nchem; v++) {
-      double c[6];
+    // per-point base pointer (and sign) of the tracer block of the cell
+    const double* cp[6];
+    double sg[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++) c[l] = load_chem<GEN>(P, pt[l], v);
-      emit(5 + v, tracer_face(c, up, um));
+    for (int l = 0; l < 6; l++) {
+      if (GEN && pt[l].src >= 0) cp[l] = P.ghost[pt[l].src].buf + pt[l].off + 5;
+      else cp[l] = P.w[5] + pt[l].off * P.nchem;
+      sg[l] = (GEN && ((pt[l].neg >> 5) & 1u)) ? -1.0 : 1.0;
+    }
+    // Tracers two at a time: one 16-byte load per stencil point feeds two independent
+    // reconstructions (four WENO chains in flight), and the next pair is loaded while the
+    // current one is reconstructed.  Needs nchem even and 16-byte aligned blocks, which
+    // holds for the owned array (species-fastest, base from cudaMalloc) whenever nchem is
+    // even; halo buffers hold NVAR = 5+nchem values per cell, so their tracer block is
+    // only 8-byte aligned and takes the scalar path.
+    bool vec = ((P.nchem & 1) == 0) && ((((unsigned long long)P.w[5]) & 15ull) == 0ull);
+    if (GEN) {
+#pragma unroll
+      for (int l = 0; l < 6; l++) vec = vec && (pt[l].src < 0);
+    }
+    if (vec) {
+      double2 c[6], cn[6];
+#pragma unroll
+      for (int l = 0; l < 6; l++) c[l] = *reinterpret_cast<const double2*>(cp[l]);
+#pragma unroll 1
+      for (int v = 0; v < P.nchem; v += 2) {
+        const int vn = (v + 2 < P.nchem) ? v + 2 : v;
+#pragma unroll
+        for (int l = 0; l < 6; l++) cn[l] = *reinterpret_cast<const double2*>(cp[l] + vn);
+        double a[6], b[6];
+#pragma unroll
+        for (int l = 0; l < 6; l++) {
+          a[l] = GEN ? c[l].x * sg[l] : c[l].x;
+          b[l] = GEN ? c[l].y * sg[l] : c[l].y;
+        }
+        const double fa = tracer_face(a, up, um);
+        const double fb = tracer_face(b, up, um);
+        emit(5 + v, fa);
+        emit(6 + v, fb);
+#pragma unroll
+        for (int l = 0; l < 6; l++) c[l] = cn[l];
+      }
+    } else {
+#pragma unroll 1
+      for (int v = 0; v < P.nchem; v++) {
+        double c[6];
+#pragma unroll
+        for (int l = 0; l < 6; l++) c[l] = GEN ? cp[l][v] * sg[l] : cp[l][v];
+        emit(5 + v, tracer_face(c, up, um));
+      }
     }
   }
   return bits;
@@ -181,7 +215,8 @@ EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, l
 
 // Dynamic shared memory: three arrays [NVAR][T] of doubles: FX, FY (exchanged with the
 // +x / +y neighbour thread) and ZLO (thread-private: flux through the z-face below).
-__global__ void rhs_fused_kernel(const RhsParams P)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
   const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;

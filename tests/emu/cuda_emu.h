@@ -30,6 +30,7 @@
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3_emu { unsigned x, y, z; };
+struct double2 { double x, y; };
 
 namespace cuda_emu {
 inline uint3_emu& tidx() { static uint3_emu v; return v; }

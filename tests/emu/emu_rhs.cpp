@@ -25,7 +25,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
   eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads);
   P.seg_len = L.seg_len;
-  cuda_emu::launch(eb::rhs_fused_kernel, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+  cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
   *state_bits = flag;
   return flag ? -1 : 0;
 }
