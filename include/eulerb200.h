@@ -69,6 +69,11 @@ int eulerb200_version(void);
 int eulerb200_decompose(int32_t nprocs, int32_t rank, const int64_t* n, const int32_t* bc,
                         int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr);
 
+/* The point-to-point operations one halo exchange issues, in issue order: the role of the
+ * Irecv/Isend tags of euler3D.hpp:608-640,663-784.  ops receives up to 12 triples
+ * (kind, face, peer) with kind 0 = send, 1 = receive; returns their number. */
+int eulerb200_exchange_plan(const eulerb200_config* cfg, int32_t* ops);
+
 /* EulerData constructor + the allocation part of SetupDecomp (euler3D.hpp:497-559):
  * owns halo slabs, streams, events and the legal-state flag.  Never allocates afterwards. */
 int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out);

@@ -48,6 +48,7 @@ ABI = {
     "eulerb200_decompose": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int32)]),
+    "eulerb200_exchange_plan": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_int32)]),
     "eulerb200_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "eulerb200_destroy": (C.c_int, [C.c_void_p]),
     "eulerb200_last_error": (C.c_char_p, [C.c_void_p]),
@@ -210,6 +211,13 @@ class EulerData:
         for f in range(5):
             c.forcing[f] = float(self.forcing[f])
         return c
+
+    def exchange_plan(self):
+        """[(kind, face, peer)] in issue order; kind 'send' / 'recv' (eulerb200_exchange_plan)."""
+        ops = (C.c_int32 * 36)()
+        cfg = self._config()
+        n = load_library().eulerb200_exchange_plan(C.byref(cfg), ops)
+        return [("send" if ops[3 * q] == 0 else "recv", int(ops[3 * q + 1]), int(ops[3 * q + 2])) for q in range(n)]
 
     def _create(self):
         lib = load_library()

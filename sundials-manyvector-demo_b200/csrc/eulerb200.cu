@@ -323,16 +323,14 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
   EB_CUDA(c, cudaGetLastError());
   EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
   EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
-  // Sends in face order W,E,S,N,B,F; receives in the order of the opposite faces, so that
-  // between any pair of ranks the k-th send meets the k-th receive (the job the tags do
-  // in euler3D.hpp:608-640,663-784).
+  eb::ExchangeOp ops[12];
+  const int nops = eb::exchange_plan(c->cfg, ops);
   EB_NCCL(c, nccl().GroupStart());
-  for (int f = 0; f < 6; f++) {
-    if (c->remote[f])
-      EB_NCCL(c, nccl().Send(c->send[f], (size_t)eb::face_len(c->cfg, f), ncclDouble, c->cfg.nbr[f], c->comm, c->comm_stream));
-    const int r = f ^ 1;
-    if (c->remote[r])
-      EB_NCCL(c, nccl().Recv(c->recv[r], (size_t)eb::face_len(c->cfg, r), ncclDouble, c->cfg.nbr[r], c->comm, c->comm_stream));
+  for (int q = 0; q < nops; q++) {
+    const int f = ops[q].face;
+    const size_t len = (size_t)eb::face_len(c->cfg, f);
+    if (ops[q].kind == 0) EB_NCCL(c, nccl().Send(c->send[f], len, ncclDouble, ops[q].peer, c->comm, c->comm_stream));
+    else EB_NCCL(c, nccl().Recv(c->recv[f], len, ncclDouble, ops[q].peer, c->comm, c->comm_stream));
   }
   EB_NCCL(c, nccl().GroupEnd());
   EB_CUDA(c, cudaEventRecord(c->ev_recv, c->comm_stream));
@@ -360,6 +358,15 @@ int eulerb200_decompose(int32_t nprocs, int32_t rank, const int64_t* n, const in
                         int32_t* dims, int32_t* coords, int64_t* ext, int32_t* nbr)
 {
   return eb::decompose(nprocs, rank, n, bc, dims, coords, ext, nbr);
+}
+
+int eulerb200_exchange_plan(const eulerb200_config* cfg, int32_t* ops)
+{
+  if (!cfg || !ops) return -1;
+  eb::ExchangeOp tmp[12];
+  const int n = eb::exchange_plan(*cfg, tmp);
+  for (int q = 0; q < n; q++) { ops[3 * q] = tmp[q].kind; ops[3 * q + 1] = tmp[q].face; ops[3 * q + 2] = tmp[q].peer; }
+  return n;
 }
 
 const char* eulerb200_last_error(const eulerb200_ctx* ctx)

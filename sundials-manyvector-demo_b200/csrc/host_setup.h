@@ -115,6 +115,22 @@ inline int ghost_face(const eulerb200_config& c, int f, const double* recv, Ghos
   return 0;
 }
 
+// Order of the point-to-point operations of one halo exchange.  Sends go out in face order
+// W,E,S,N,B,F; the receive posted next to the send of face f is the one for the OPPOSITE
+// face f^1.  Between any two ranks the k-th send of one then meets the k-th receive of the
+// other, which is what the message tags do in the reference (euler3D.hpp:608-640,663-784).
+struct ExchangeOp { int32_t kind, face, peer; };   // kind 0 = send, 1 = recv
+inline int exchange_plan(const eulerb200_config& c, ExchangeOp* ops)
+{
+  int n = 0;
+  for (int f = 0; f < 6; f++) {
+    if (face_is_remote(c, f)) { ops[n].kind = 0; ops[n].face = f; ops[n].peer = c.nbr[f]; n++; }
+    const int r = f ^ 1;
+    if (face_is_remote(c, r)) { ops[n].kind = 1; ops[n].face = r; ops[n].peer = c.nbr[r]; n++; }
+  }
+  return n;
+}
+
 struct LaunchGeom {
   unsigned gx, gy, gz;
   int tx, ty;

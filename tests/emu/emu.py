@@ -1,0 +1,55 @@
+"""TEST INFRASTRUCTURE.  Builds tests/emu/libemu.so (the product's kernel SOURCE compiled
+for the CPU through cuda_emu.h) and calls it.  Never imported by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "sundials-manyvector-demo_b200", "csrc")
+SO = os.path.join(HERE, "libemu.so")
+_dp = C.POINTER(C.c_double)
+
+
+def build():
+    deps = [os.path.join(HERE, f) for f in ("emu_rhs.cpp", "cuda_emu.h")] + \
+           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "euler_math.cuh", "host_setup.h")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-ffp-contract=off",
+                               "-o", SO, os.path.join(HERE, "emu_rhs.cpp")])
+    return SO
+
+
+def _ptrs(arrs):
+    out = (_dp * 6)()
+    for i in range(6):
+        a = arrs[i] if arrs is not None and i < len(arrs) else None
+        out[i] = a.ctypes.data_as(_dp) if a is not None and a.size else None
+    return out
+
+
+class Emu:
+    def __init__(self, pkg):
+        self.pkg = pkg
+        self.lib = C.CDLL(build())
+        self.lib.emu_rhs.restype = C.c_int
+
+    def rhs(self, n, nchem, d, gamma, bcs, nbr, rank, w, forcing=None, recv=None, lo=None, hi=None, threads=256):
+        c = self.pkg.Config()
+        c.nxl, c.nyl, c.nzl = n
+        c.nchem, c.device = nchem, -1
+        c.dx, c.dy, c.dz, c.gamma = d[0], d[1], d[2], gamma
+        for f in range(6):
+            c.bc[f], c.nbr[f] = bcs[f], nbr[f]
+        c.rank, c.nranks = rank, 1
+        for f in range(5):
+            c.forcing[f] = forcing[f] if forcing is not None else 0.0
+        N = n[0] * n[1] * n[2]
+        out = [np.full(N, np.nan) for _ in range(5)] + [np.full(N * nchem, np.nan) if nchem else None]
+        bits = C.c_int(0)
+        L3 = C.c_long * 3
+        ret = self.lib.emu_rhs(C.byref(c), _ptrs(w), _ptrs(out), _ptrs(recv) if recv is not None else None,
+                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads)
+        return ret, out, bits.value

@@ -1,0 +1,86 @@
+"""Multi-GPU tier (needs >= 2 B200s; skipped otherwise): the decomposed CUDA RHS with NCCL
+halo exchange and interior/boundary overlap must equal the single-rank oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P, N, D, R = 0, 1, 2, 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port_no, n, nchem, bcs, outdir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from __graft_entry__ import load_package
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    pkg = load_package()
+    u = pkg.EulerData(nchem=nchem)
+    u.nx, u.ny, u.nz = n
+    u.xlbc, u.xrbc, u.ylbc, u.yrbc, u.zlbc, u.zrbc = bcs
+    u.forcing = [0, 0, -0.1, 0, 0]
+    assert u.SetupDecomp(myid=rank, nprocs=world, device=rank) == 0
+    w = oracle.random_state(n, nchem, seed=31)
+    W3 = [w[f].reshape(n[2], n[1], n[0]) for f in range(5)] + ([w[5].reshape(n[2], n[1], n[0], nchem)] if nchem else [])
+    sl = (slice(u.ks, u.ke + 1), slice(u.js, u.je + 1), slice(u.is_, u.ie + 1))
+    wl = pkg.ManyVector([torch.from_numpy(np.ascontiguousarray(a[sl]).ravel()).cuda() for a in W3])
+    wdot = pkg.ManyVector.new(u)
+    for _ in range(2):       # twice: buffers and events must be reusable
+        assert pkg.fEuler(0.0, wl, wdot, u) == 0, u.last_error()
+    u.cfl = 0.4
+    ret, dt = pkg.stability(wl, 0.0, u)
+    assert ret == 0
+    np.savez(os.path.join(outdir, "rank%d.npz" % rank), ext=np.array([u.is_, u.ie, u.js, u.je, u.ks, u.ke]),
+             dt=dt, **{"wdot%d" % f: s.cpu().numpy() for f, s in enumerate(wdot.sub)})
+    dist.barrier()
+    u.FreeData()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,nchem,bcs", [
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N]),
+    (2, (3, 40, 36), 0, [N] * 6),
+    (4, (24, 28, 20), 2, [P] * 6),
+    (8, (24, 24, 24), 10, [R] * 6),
+    (8, (3, 64, 48), 0, [N] * 6),
+])
+def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem, bcs):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import oracle
+    mp.spawn(_worker, args=(world, _free_port(), n, nchem, bcs, str(tmp_path)), nprocs=world, join=True)
+    port = oracle.Port()
+    w = oracle.random_state(n, nchem, seed=31)
+    d = (1.0 / n[0], 1.0 / n[1], 1.0 / n[2])
+    cfg = port.cfg(n, nchem, d, 1.4, bcs, forcing=[0, 0, -0.1, 0, 0])
+    ret, ref, _ = port.feuler(cfg, w)
+    assert ret == 0
+    dt_want = port.dt_stab(cfg, 0.4, port.max_wavespeed(cfg, w))
+    R3 = [ref[f].reshape(n[2], n[1], n[0]) for f in range(5)] + ([ref[5].reshape(n[2], n[1], n[0], nchem)] if nchem else [])
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        e = z["ext"]
+        sl = (slice(e[4], e[5] + 1), slice(e[2], e[3] + 1), slice(e[0], e[1] + 1))
+        assert float(z["dt"]) == pytest.approx(dt_want, rel=1e-14)
+        for f, a in enumerate(R3):
+            want = np.ascontiguousarray(a[sl]).ravel()
+            assert np.abs(z["wdot%d" % f] - want).max() <= 1e-12 * np.abs(a).max()

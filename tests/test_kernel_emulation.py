@@ -1,0 +1,94 @@
+"""CPU-side logic tests of the CUDA kernel SOURCE (rhs_kernel.cuh + host_setup.h compiled
+through tests/emu/cuda_emu.h): ghost maps, shared-memory exchange, barrier placement,
+sub-box launches and halo-buffer reads, against the oracle.  The emulation is test
+infrastructure only -- the product has no CPU path; the real parity tests are the
+``-m gpu`` ones.  Tolerance as there: normwise 1e-12."""
+import numpy as np
+import pytest
+
+from conftest import normwise_errors
+
+P, N, D, R = 0, 1, 2, 3
+NO = -1
+
+
+@pytest.fixture(scope="module")
+def emu(pkg):
+    from emu.emu import Emu
+    return Emu(pkg)
+
+
+def nbr_single(bcs):
+    return [0 if b == P else NO for b in bcs]
+
+
+@pytest.mark.parametrize("n,nchem,bcs,threads", [
+    ((12, 9, 7), 0, [P] * 6, 256),
+    ((12, 9, 7), 2, [N] * 6, 384),
+    ((12, 9, 7), 3, [R] * 6, 256),          # odd nchem: scalar tracer path
+    ((35, 10, 5), 2, [P, P, R, R, N, N], 128),
+    ((3, 20, 17), 2, [N] * 6, 256),          # thin x
+    ((40, 3, 3), 0, [N] * 6, 256),           # sod_x shape
+    ((7, 6, 26), 4, [R, R, P, P, N, N], 64), # several z-segments
+])
+def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, threads):
+    w = oracle_mod.random_state(n, nchem, seed=sum(n))
+    d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+    forcing = [0, 0, -0.1, 0, 0]
+    ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads)
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
+    assert ret == 0 and ret_ref == 0 and bits == 0
+    assert max(normwise_errors(got, ref)) <= 1e-12
+
+
+def test_emulated_illegal_state_bits(emu, oracle_mod, port):
+    n = (10, 8, 6)
+    w = oracle_mod.random_state(n, 0, seed=2)
+    w[4][33] = -5.0
+    ret, _, bits = emu.rhs(n, 0, (0.1, 0.1, 0.1), 1.4, [P] * 6, [0] * 6, 0, w)
+    _, _, mask = port.feuler(port.cfg(n, 0, (0.1, 0.1, 0.1), 1.4, [P] * 6), w)
+    assert ret == -1 and bits == mask == 6
+
+
+def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle_mod, port):
+    """The N>1 kernel path without a GPU: split a periodic/reflecting box over 2 ranks the way
+    SetupDecomp does, hand each rank the neighbour's packed layers as its halo buffers
+    (wire layout of euler3D.hpp:648), evaluate interior and boundary shells as separate
+    sub-box launches exactly like eulerb200_rhs_async, and compare with the global oracle."""
+    n, nchem = (14, 8, 6), 2
+    bcs = [P, P, R, R, N, N]
+    d = (0.1, 0.2, 0.3)
+    w = oracle_mod.random_state(n, nchem, seed=21)
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+    W3 = [w[f].reshape(n[2], n[1], n[0]) for f in range(5)] + [w[5].reshape(n[2], n[1], n[0], nchem)]
+    R3 = [ref[f].reshape(n[2], n[1], n[0]) for f in range(5)] + [ref[5].reshape(n[2], n[1], n[0], nchem)]
+    blocks = []
+    for rank in range(2):
+        rc, dims, coords, ext, nbr = pkg.dims_and_extents(2, rank, n, bcs)
+        assert rc == 0 and dims == [2, 1, 1]
+        sl = (slice(ext[4], ext[5] + 1), slice(ext[2], ext[3] + 1), slice(ext[0], ext[1] + 1))
+        parts = [np.ascontiguousarray(a[sl]).ravel() for a in W3]
+        nl = (ext[1] - ext[0] + 1, ext[3] - ext[2] + 1, ext[5] - ext[4] + 1)
+        blocks.append(dict(ext=ext, nbr=nbr, parts=parts, nl=nl, sl=sl))
+    for rank, b in enumerate(blocks):
+        other = blocks[1 - rank]
+        ocfg = port.cfg(other["nl"], nchem, d, 1.4, bcs)
+        recv = [None] * 6
+        for f in range(6):
+            if b["nbr"][f] not in (NO, rank):
+                recv[f] = port.pack_send(ocfg, other["parts"], f ^ 1)
+        nl = b["nl"]
+        out = [np.full(nl[0] * nl[1] * nl[2], np.nan) for _ in range(5)] + [np.full(nl[0] * nl[1] * nl[2] * nchem, np.nan)]
+        lo = [3 if b["nbr"][2 * a] not in (NO, rank) else 0 for a in range(3)]
+        hi = [nl[a] - (3 if b["nbr"][2 * a + 1] not in (NO, rank) else 0) for a in range(3)]
+        boxes = [(lo, hi), ([0, lo[1], lo[2]], [lo[0], hi[1], hi[2]]), ([hi[0], lo[1], lo[2]], [nl[0], hi[1], hi[2]])]
+        for blo, bhi in boxes:
+            ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi)
+            assert ret == 0
+            for o, p_ in zip(out, part):
+                m = ~np.isnan(p_)
+                assert np.all(np.isnan(o[m]))       # shells do not overlap
+                o[m] = p_[m]
+        want = [np.ascontiguousarray(a[b["sl"]]).ravel() for a in R3]
+        assert not any(np.isnan(o).any() for o in out)
+        assert max(normwise_errors(out, want)) <= 1e-12
