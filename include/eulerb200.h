@@ -106,6 +106,11 @@ int eulerb200_state_flag(eulerb200_ctx* ctx, void* stream, int32_t* bits);
 int eulerb200_rhs_host(eulerb200_ctx* ctx, double t, const double* const* w_host,
                        double* const* wdot_host);
 
+/* Dispatch on where w lives (device/managed -> eulerb200_rhs, host -> eulerb200_rhs_host);
+ * what a drop-in fEuler that is handed arbitrary N_Vectors calls. */
+int eulerb200_rhs_any(eulerb200_ctx* ctx, double t, const double* const* w, double* const* wdot,
+                      void* stream);
+
 /* EulerData::ExchangeStart / ExchangeEnd (euler3D.hpp:577-1191), callable on their own. */
 int eulerb200_exchange_start(eulerb200_ctx* ctx, const double* const* w, void* stream);
 int eulerb200_exchange_end(eulerb200_ctx* ctx, void* stream);
@@ -121,6 +126,10 @@ int eulerb200_ghost_face(eulerb200_ctx* ctx, const double* const* w, int32_t fac
  * max taken over all ranks.  Synchronous (returns the value). */
 int eulerb200_stability(eulerb200_ctx* ctx, const double* const* w, double cfl, double* dt_stab,
                         void* stream);
+
+/* Same, dispatching on where w lives (host arrays are staged to the device first). */
+int eulerb200_stability_any(eulerb200_ctx* ctx, const double* const* w, double cfl, double* dt_stab,
+                            void* stream);
 
 /* Number of kernel launches issued through this context so far. */
 int64_t eulerb200_launch_count(const eulerb200_ctx* ctx);

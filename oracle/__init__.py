@@ -50,6 +50,15 @@ def build_ref(nvars=NVARS):
     return True
 
 
+def build_dropin():
+    """Link check of the drop-in fEuler against the reference's own EulerData (needs the
+    reference tree and the built libeulerb200.so); binaries land in oracle/_ref."""
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        return False
+    subprocess.check_call(["make", "-s", "-C", HERE, "dropin", "REFERENCE=" + REFERENCE_ROOT])
+    return True
+
+
 def have_ref(nvar=5):
     return os.path.exists(os.path.join(REF_DIR, "libref_nvar%d.so" % nvar))
 

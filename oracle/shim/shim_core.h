@@ -101,6 +101,7 @@ struct MPI_Status { int MPI_SOURCE, MPI_TAG, MPI_ERROR; };
 #define MPI_DOUBLE 1
 #define MPI_LONG 2
 #define MPI_INT 3
+#define MPI_BYTE 4
 #define MPI_SUNREALTYPE MPI_DOUBLE
 #define MPI_SUM 1
 #define MPI_MIN 2
@@ -124,6 +125,7 @@ int MPI_Isend(const void* buf, int count, MPI_Datatype, int dst, int tag, MPI_Co
 int MPI_Waitall(int n, MPI_Request* req, MPI_Status* stat);
 int MPI_Allreduce(const void* in, void* out, int count, MPI_Datatype, MPI_Op, MPI_Comm);
 int MPI_Barrier(MPI_Comm);
+int MPI_Bcast(void* buf, int count, MPI_Datatype, int root, MPI_Comm);
 int MPI_Abort(MPI_Comm, int code);
 double MPI_Wtime(void);
 

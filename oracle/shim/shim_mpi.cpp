@@ -160,6 +160,17 @@ int MPI_Allreduce(const void* in, void* out, int count, MPI_Datatype, MPI_Op op,
   return MPI_SUCCESS;
 }
 
+int MPI_Bcast(void* buf, int count, MPI_Datatype type, int root, MPI_Comm comm)
+{
+  static std::vector<char> box;
+  const size_t bytes = (size_t)count * (type == MPI_BYTE ? 1 : (type == MPI_INT ? 4 : 8));
+  if (t_rank == root) { std::lock_guard<std::mutex> lk(g_mtx); box.assign((char*)buf, (char*)buf + bytes); }
+  MPI_Barrier(comm);
+  if (t_rank != root) { std::lock_guard<std::mutex> lk(g_mtx); memcpy(buf, box.data(), bytes); }
+  MPI_Barrier(comm);
+  return MPI_SUCCESS;
+}
+
 int MPI_Abort(MPI_Comm, int code) { fprintf(stderr, "shim MPI_Abort(%d)\n", code); abort(); return 0; }
 
 double MPI_Wtime(void) {

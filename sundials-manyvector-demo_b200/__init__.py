@@ -58,11 +58,13 @@ ABI = {
     "eulerb200_rhs_async": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_state_flag": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "eulerb200_rhs_host": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6]),
+    "eulerb200_rhs_any": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_exchange_start": (C.c_int, [C.c_void_p, _vp6, C.c_void_p]),
     "eulerb200_exchange_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eulerb200_face_len": (C.c_int64, [C.c_void_p, C.c_int32]),
     "eulerb200_ghost_face": (C.c_int, [C.c_void_p, _vp6, C.c_int32, C.c_void_p, C.c_void_p]),
     "eulerb200_stability": (C.c_int, [C.c_void_p, _vp6, C.c_double, C.POINTER(C.c_double), C.c_void_p]),
+    "eulerb200_stability_any": (C.c_int, [C.c_void_p, _vp6, C.c_double, C.POINTER(C.c_double), C.c_void_p]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),
     "eulerb200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }

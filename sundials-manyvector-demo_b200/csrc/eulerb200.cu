@@ -346,6 +346,28 @@ int exchange_end(eulerb200_ctx* c, cudaStream_t s)
   return 0;
 }
 
+int ensure_staging(eulerb200_ctx* c)
+{
+  if (c->host_ready) return 0;
+  const eulerb200_config& g = c->cfg;
+  const long N = g.nxl * g.nyl * g.nzl;
+  const int nsub = 5 + (g.nchem > 0 ? 1 : 0);
+  for (int f = 0; f < nsub; f++) {
+    const size_t bytes = sizeof(double) * N * (f < 5 ? 1 : g.nchem);
+    EB_CUDA(c, cudaMalloc(&c->stage_w[f], bytes));
+    EB_CUDA(c, cudaMalloc(&c->stage_wdot[f], bytes));
+  }
+  EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+  EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int s = 0; s < eulerb200_ctx::kMaxSlabs; s++) {
+    EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_up[s], cudaEventDisableTiming));
+    EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
+  }
+  c->host_ready = true;
+  return 0;
+}
+
 }  // namespace
 
 // ------------------------------------- C ABI -------------------------------------
@@ -597,21 +619,7 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
   const long plane = g.nxl * g.nyl, N = plane * g.nzl;
   const int nsub = 5 + (g.nchem > 0 ? 1 : 0);
   EB_CUDA(c, cudaSetDevice(c->device));
-  if (!c->host_ready) {
-    for (int f = 0; f < nsub; f++) {
-      const size_t bytes = sizeof(double) * N * (f < 5 ? 1 : g.nchem);
-      EB_CUDA(c, cudaMalloc(&c->stage_w[f], bytes));
-      EB_CUDA(c, cudaMalloc(&c->stage_wdot[f], bytes));
-    }
-    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
-    EB_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-    for (int s = 0; s < eulerb200_ctx::kMaxSlabs; s++) {
-      EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_up[s], cudaEventDisableTiming));
-      EB_CUDA(c, cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
-    }
-    c->host_ready = true;
-  }
+  { int rc_ = ensure_staging(c); if (rc_) return rc_; }
   if (c->any_remote) {
     // with remote neighbours the halo exchange needs the whole state: no slab pipeline
     for (int f = 0; f < nsub; f++)
@@ -666,6 +674,16 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
   return 0;
 }
 
+int eulerb200_rhs_any(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* stream)
+{
+  if (!c || !w || !wdot || !w[0]) return -1;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, w[0]);
+  if (e != cudaSuccess) { cudaGetLastError(); return eulerb200_rhs_host(c, t, w, wdot); }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return eulerb200_rhs(c, t, w, wdot, stream);
+  return eulerb200_rhs_host(c, t, w, wdot);
+}
+
 int eulerb200_stability(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void* stream)
 {
   if (!c || !w || !dt_stab) return -1;
@@ -683,6 +701,22 @@ int eulerb200_stability(eulerb200_ctx* c, const double* const* w, double cfl, do
   const double h = std::min(std::min(c->cfg.dx, c->cfg.dy), c->cfg.dz);
   *dt_stab = cfl * h / *c->h_alpha;   // utilities.cpp:520
   return 0;
+}
+
+int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void* stream)
+{
+  if (!c || !w || !w[0]) return -1;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, w[0]);
+  if (e != cudaSuccess) cudaGetLastError();
+  if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+    return eulerb200_stability(c, w, cfl, dt_stab, stream);
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
+  for (int f = 0; f < 5; f++)
+    EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f], w[f], sizeof(double) * N, cudaMemcpyHostToDevice, c->s_cmp));
+  return eulerb200_stability(c, c->stage_w, cfl, dt_stab, c->s_cmp);
 }
 
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
