@@ -62,17 +62,18 @@ EB_HD double fast_rcp(double b)
 // with q1-q2 = -(D1-D2)/6 and q3-q2 = (D3-D2)/3 (D_k the second differences).
 EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
 {
-  const double bc = 13.0 / 12.0;
-  const double eps4 = 4.0 * 1e-6;
+  // beta_k/bc = D_k^2 + (0.25/bc) E_k^2; the common factor 1/bc cancels in the weight ratios
+  const double c2 = 0.25 / (13.0 / 12.0);
+  const double epsb = (4.0 * 1e-6) / (13.0 / 12.0);
   const double D1 = fma(-2.0, v3, v2) + v4;
   const double D2 = fma(-2.0, v2, v1) + v3;
   const double D3 = fma(-2.0, v1, v0) + v2;
   const double E1 = fma(3.0, v2, fma(-4.0, v3, v4));
   const double E2 = v1 - v3;
   const double E3 = fma(3.0, v2, fma(-4.0, v1, v0));
-  const double b1 = fma(bc, D1 * D1, fma(0.25, E1 * E1, eps4));
-  const double b2 = fma(bc, D2 * D2, fma(0.25, E2 * E2, eps4));
-  const double b3 = fma(bc, D3 * D3, fma(0.25, E3 * E3, eps4));
+  const double b1 = fma(D1, D1, fma(c2 * E1, E1, epsb));
+  const double b2 = fma(D2, D2, fma(c2 * E2, E2, epsb));
+  const double b3 = fma(D3, D3, fma(c2 * E3, E3, epsb));
   const double s1 = b1 * b1, s2 = b2 * b2, s3 = b3 * b3;
   const double P1 = s2 * s3, P2 = s1 * s3, P3 = s1 * s2;
   const double den = fma(0.3, P1, fma(0.6, P2, 0.1 * P3));
@@ -101,41 +102,57 @@ EB_HD void project(const Eigen& E, double x0, double x1, double x2, double x3, d
   y3 = -E.gc * fma(E.q - E.H, x0, S);
 }
 
+// Per-cell quantities every face that touches the cell needs (each cell sits in 18
+// stencils per RHS): 1/rho, pressure (euler3D.hpp:1383-1388), sound speed
+// sqrt(gamma p / rho) and sqrt(rho), the last two with SUNRsqrt semantics.  Computed once
+// per cell by aux_kernel into four arrays; on the fly for ghost/halo points.
+struct CellAux { double rinv, p, c, sr; };
+EB_HD CellAux cell_aux(double gamma, double r, double mx, double my, double mz, double e)
+{
+  CellAux a;
+  a.rinv = fast_rcp(r);
+  const double m2sum = fma(mz, mz, fma(my, my, mx * mx));
+  a.p = (gamma - 1.0) * fma(-0.5 * m2sum, a.rinv, e);
+  a.c = sun_sqrt(gamma * a.p * a.rinv);
+  a.sr = sun_sqrt(r);
+  return a;
+}
+
 // Six-point stencil of the five fluid fields in sweep-aligned order: mn is the
 // momentum normal to the face, m1/m2 the tangential ones in the order the reference's
-// swap leaves them (utilities.cpp:283-285: x:(mx,my,mz)  y:(my,mx,mz)  z:(mz,my,mx)).
+// swap leaves them (utilities.cpp:283-285: x:(mx,my,mz)  y:(my,mx,mz)  z:(mz,my,mx)),
+// plus the per-cell derived values (sr only for the two cells adjacent to the face).
 struct FluidStencil {
   double r[6], mn[6], m1[6], m2[6], e[6];
+  double rinv[6], p[6], c[6];
+  double srL, srR;
 };
 
 // Fluid part of one face.  Returns through `f` the five face fluxes in sweep-aligned
 // order (rho, normal, tan1, tan2, energy), and through alpha / u[6] what the tracers
-// of the same face need (face-local max wave speed, normal velocity per point); p3_out is
-// the pressure of stencil point 3 (the cell above the face), for the legal_state check.
-EB_HD void fluid_face(const FluidStencil& s, double gamma, double f[5], double& alpha_out, double u[6],
-                       double& p3_out)
+// of the same face need (face-local max wave speed, normal velocity per point).
+EB_HD void fluid_face(const FluidStencil& s, double gamma, double f[5], double& alpha_out, double u[6])
 {
   const double gm1 = gamma - 1.0;
-  double p[6];
+  const double* p = s.p;
   double alpha = 0.0;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    const double rinv = fast_rcp(s.r[j]);
-    u[j] = s.mn[j] * rinv;
-    const double m2sum = fma(s.m2[j], s.m2[j], fma(s.m1[j], s.m1[j], s.mn[j] * s.mn[j]));
-    p[j] = gm1 * fma(-0.5 * m2sum, rinv, s.e[j]);
-    const double a = fabs(u[j]) + sun_sqrt(gamma * p[j] * rinv);
+    u[j] = s.mn[j] * s.rinv[j];
+    const double a = fabs(u[j]) + s.c[j];
     alpha = (alpha < a) ? a : alpha;
   }
   alpha_out = alpha;
-  p3_out = p[3];
 
   // Roe average of the two cells adjacent to the face (utilities.cpp:298-304):
-  // 0.5*(a/sL + b/sR)/(0.5*(sL+sR)) = (a/sL + b/sR)/(sL+sR)
+  // 0.5*(a/sL + b/sR)/(0.5*(sL+sR)) = (a/sL + b/sR)/(sL+sR), and 1/sqrt(rho) = sqrt(rho)/rho.
+  // A non-positive density gives sL = 0 in the reference and a division by it: keep that
+  // non-finite (the Dirichlet-ghost corner).
   Eigen E;
   {
-    const double sL = sun_sqrt(s.r[2]), sR = sun_sqrt(s.r[3]);
-    const double isL = fast_rcp(sL), isR = fast_rcp(sR), iS = fast_rcp(sL + sR);
+    const double isL = (s.srL > 0.0) ? s.srL * s.rinv[2] : nan("");
+    const double isR = (s.srR > 0.0) ? s.srR * s.rinv[3] : nan("");
+    const double iS = fast_rcp(s.srL + s.srR);
     E.u = fma(s.mn[2], isL, s.mn[3] * isR) * iS;
     E.v = fma(s.m1[2], isL, s.m1[3] * isR) * iS;
     E.w = fma(s.m2[2], isL, s.m2[3] * isR) * iS;

@@ -220,6 +220,8 @@ struct eulerb200_ctx {
   bool host_ready = false;
   size_t max_smem_set = 0;
   int variant = 0;
+  double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
+  bool use_aux = true;
 };
 
 namespace {
@@ -273,6 +275,7 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
     P.wdot[f] = (f < 5 || g.nchem > 0) ? wdot[f] : nullptr;
     eb::ghost_face(g, f, c->recv[f], &P.ghost[f]);
   }
+  for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
   P.state_flag = c->d_flag;
   P.lo[0] = P.lo[1] = P.lo[2] = 0;
   P.hi[0] = P.nx; P.hi[1] = P.ny; P.hi[2] = P.nz;
@@ -295,6 +298,18 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     c->max_smem_set = L.smem;
   }
   V.fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+// Per-cell derived values for the z-planes [k0, k1) of the state in P.
+int launch_aux(eulerb200_ctx* c, const eb::RhsParams& P, long k0, long k1, cudaStream_t s)
+{
+  if (!c->use_aux || k1 <= k0) return 0;
+  const long plane = P.nx * P.ny, c0 = k0 * plane, c1 = k1 * plane;
+  const unsigned blocks = (unsigned)std::min<long>((c1 - c0 + 255) / 256, 148L * 16);
+  eb::aux_kernel<<<blocks, 256, 0, s>>>(P, c->aux[0], c->aux[1], c->aux[2], c->aux[3], c0, c1);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
@@ -438,6 +453,10 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMallocHost(&c->h_flag, sizeof(int)));
   EB_CREATE(cudaMalloc(&c->d_alpha, sizeof(unsigned long long)));
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
+  if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
+  if (c->use_aux)
+    for (int q = 0; q < 4; q++)
+      EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));
   for (int f = 0; f < 6; f++) {
     c->remote[f] = eb::face_is_remote(*cfg, f);
     if (c->remote[f]) {
@@ -475,6 +494,7 @@ int eulerb200_destroy(eulerb200_ctx* c)
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
   if (c->ev_recv) cudaEventDestroy(c->ev_recv);
+  for (int q = 0; q < 4; q++) if (c->aux[q]) cudaFree(c->aux[q]);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->d_alpha) cudaFree(c->d_alpha);
@@ -544,6 +564,10 @@ int eulerb200_rhs_async(eulerb200_ctx* c, double t, const double* const* w, doub
   EB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), s));
   const eb::RhsParams P = make_params(c, w, wdot);
   const long n[3] = {P.nx, P.ny, P.nz};
+  {
+    int rc_ = launch_aux(c, P, 0, P.nz, s);
+    if (rc_) return rc_;
+  }
   if (!c->any_remote) {
     const long lo[3] = {0, 0, 0};
     return launch_box(c, P, lo, n, s);
@@ -646,10 +670,15 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
     }
     const bool wrap = (g.nbr[4] == g.rank);
     const eb::RhsParams P = make_params(c, c->stage_w, c->stage_wdot);
+    int aux_done = 0;     // slabs whose per-cell derived values are computed
     for (int q = 0; q < S; q++) {
       const int s = wrap ? (q + 1) % S : q;
       const int need = (wrap && s == 0) ? S - 1 : std::min(s + 1, S - 1);
       EB_CUDA(c, cudaStreamWaitEvent(c->s_cmp, c->ev_up[need], 0));
+      for (; aux_done <= need; aux_done++) {
+        int rc_ = launch_aux(c, P, zb[aux_done], zb[aux_done + 1], c->s_cmp);
+        if (rc_) return rc_;
+      }
       const long lo[3] = {0, 0, zb[s]}, hi[3] = {g.nxl, g.nyl, zb[s + 1]};
       int rc = launch_box(c, P, lo, hi, c->s_cmp);
       if (rc) return rc;

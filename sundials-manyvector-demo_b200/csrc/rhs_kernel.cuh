@@ -52,6 +52,8 @@ struct RhsParams {
   const double* w[6];       // rho, mx, my, mz, et (SoA), chem (AoS, species fastest)
   double* wdot[6];
   GhostFace ghost[6];       // W,E,S,N,B,F
+  const double* aux[4];     // per-cell 1/rho, p, c, sqrt(rho) from aux_kernel (or all NULL:
+                            // everything derived on the fly)
   int* state_flag;          // OR of legal_state failure bits (euler3D.hpp:1405-1414)
   // sub-box of cells to evaluate: [lo, hi) per axis (the whole box for a single launch;
   // interior / boundary shells when the halo exchange is overlapped)
@@ -135,10 +137,30 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     s.m2[l] = load_fluid<GEN>(P, pt[l], f2);
     s.e[l] = load_fluid<GEN>(P, pt[l], 4);
   }
+  // Per-cell derived values: interior CTAs read what aux_kernel stored; CTAs that touch
+  // ghost or halo points derive them from the (sign-mapped) state they just loaded.
+  if (!GEN && P.aux[0] != nullptr) {
+#pragma unroll
+    for (int l = 0; l < 6; l++) {
+      s.rinv[l] = P.aux[0][pt[l].off];
+      s.p[l] = P.aux[1][pt[l].off];
+      s.c[l] = P.aux[2][pt[l].off];
+    }
+    s.srL = P.aux[3][pt[2].off];
+    s.srR = P.aux[3][pt[3].off];
+  } else {
+#pragma unroll
+    for (int l = 0; l < 6; l++) {
+      const CellAux a = cell_aux(P.gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
+      s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
+      if (l == 2) s.srL = a.sr;
+      if (l == 3) s.srR = a.sr;
+    }
+  }
 
-  double f[5], alpha, u[6], p3;
-  fluid_face(s, P.gamma, f, alpha, u, p3);
-  const int bits = ((s.r[3] > 0.0) ? 0 : 1) | ((s.e[3] > 0.0) ? 0 : 2) | ((p3 > 0.0) ? 0 : 4);
+  double f[5], alpha, u[6];
+  fluid_face(s, P.gamma, f, alpha, u);
+  const int bits = ((s.r[3] > 0.0) ? 0 : 1) | ((s.e[3] > 0.0) ? 0 : 2) | ((s.p[3] > 0.0) ? 0 : 4);
 
   emit(0, f[0]);
   emit(fn, f[1]);
@@ -212,6 +234,17 @@ EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, l
 }
 
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
+
+// Pre-pass: per-cell 1/rho, p, c, sqrt(rho) for the cells [c0, c1) (40 B read, 32 B written
+// per cell), so that the 18 stencils a cell sits in do not each redo a reciprocal and two
+// square roots on the FP64 pipe.
+__global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2, double* a3, long c0, long c1)
+{
+  for (long c = c0 + (long)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (long)gridDim.x * blockDim.x) {
+    const CellAux a = cell_aux(P.gamma, P.w[0][c], P.w[1][c], P.w[2][c], P.w[3][c], P.w[4][c]);
+    a0[c] = a.rinv; a1[c] = a.p; a2[c] = a.c; a3[c] = a.sr;
+  }
+}
 
 // Dynamic shared memory: three arrays [NVAR][T] of doubles: FX, FY (exchanged with the
 // +x / +y neighbour thread) and ZLO (thread-private: flux through the z-face below).

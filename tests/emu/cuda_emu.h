@@ -100,6 +100,8 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
         }
       }
 }
+// grid-stride "for each cell" helper for trivially parallel pre-pass kernels
+template <class F> void launch_aux_like(F f, long n) { for (long c = 0; c < n; c++) f(c); }
 }  // namespace cuda_emu
 
 #define threadIdx (cuda_emu::tidx())

@@ -8,9 +8,10 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads)
+                       int threads, int use_aux)
 {
   eb::RhsParams P;
+  std::vector<double> aux[4];
   P.nx = cfg->nxl; P.ny = cfg->nyl; P.nz = cfg->nzl;
   P.nchem = cfg->nchem;
   P.gamma = cfg->gamma;
@@ -19,6 +20,16 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   for (int f = 0; f < 6; f++) { P.w[f] = w[f]; P.wdot[f] = wdot[f]; }
   for (int f = 0; f < 6; f++)
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
+  for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
+  if (use_aux) {
+    const long N = P.nx * P.ny * P.nz;
+    for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);
+    cuda_emu::launch_aux_like([&](long c) {
+      const eb::CellAux a = eb::cell_aux(P.gamma, w[0][c], w[1][c], w[2][c], w[3][c], w[4][c]);
+      aux[0][c] = a.rinv; aux[1][c] = a.p; aux[2][c] = a.c; aux[3][c] = a.sr;
+    }, N);
+    for (int q = 0; q < 4; q++) P.aux[q] = aux[q].data();
+  }
   int flag = 0;
   P.state_flag = &flag;
   const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};

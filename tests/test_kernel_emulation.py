@@ -6,7 +6,7 @@ infrastructure only -- the product has no CPU path; the real parity tests are th
 import numpy as np
 import pytest
 
-from conftest import normwise_errors
+from conftest import normwise_errors, rounding_floor
 
 P, N, D, R = 0, 1, 2, 3
 NO = -1
@@ -30,6 +30,7 @@ def nbr_single(bcs):
     ((3, 20, 17), 2, [N] * 6, 256),          # thin x
     ((40, 3, 3), 0, [N] * 6, 256),           # sod_x shape
     ((7, 6, 26), 4, [R, R, P, P, N, N], 64), # several z-segments
+    ((70, 12, 10), 2, [P] * 6, 128),         # interior CTAs: the no-ghost path reading aux arrays
 ])
 def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, threads):
     w = oracle_mod.random_state(n, nchem, seed=sum(n))
@@ -38,7 +39,11 @@ def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, th
     ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads)
     ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
     assert ret == 0 and ret_ref == 0 and bits == 0
-    assert max(normwise_errors(got, ref)) <= 1e-12
+    floor = rounding_floor(w, 1.4, d)
+    assert max(normwise_errors(got, ref, floor)) <= 1e-12
+    # same answer with every derived value computed on the fly (no aux arrays)
+    ret, got2, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, use_aux=0)
+    assert ret == 0 and max(normwise_errors(got2, ref, floor)) <= 1e-12
 
 
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
