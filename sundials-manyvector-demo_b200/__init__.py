@@ -65,6 +65,10 @@ ABI = {
     "eulerb200_ghost_face": (C.c_int, [C.c_void_p, _vp6, C.c_int32, C.c_void_p, C.c_void_p]),
     "eulerb200_stability": (C.c_int, [C.c_void_p, _vp6, C.c_double, C.POINTER(C.c_double), C.c_void_p]),
     "eulerb200_stability_any": (C.c_int, [C.c_void_p, _vp6, C.c_double, C.POINTER(C.c_double), C.c_void_p]),
+    "eulerb200_vec_lincomb": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_void_p),
+                                       C.c_void_p, C.c_int64, C.c_void_p]),
+    "eulerb200_vec_wrms_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                          C.c_int64, C.c_void_p, C.c_void_p]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),
     "eulerb200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }
@@ -325,6 +329,15 @@ def stability(w, t, user_data):
     dt = C.c_double(0.0)
     ret = lib.eulerb200_stability(u._ctx, w.pointers(), float(u.cfl), C.byref(dt), u._stream())
     return ret, dt.value
+
+
+def __getattr__(name):
+    """Lazy sub-modules: ``driver`` (explicit time stepping) and
+    ``problems`` (initial conditions / diagnostics, 8(f-2), 8(f-4))."""
+    if name in ("driver", "problems"):
+        import importlib
+        return importlib.import_module(__name__ + "." + name)
+    raise AttributeError(name)
 
 
 def check_flag(flag, funcname, opt):

@@ -174,6 +174,47 @@ __global__ void wavespeed_kernel(const double* __restrict__ rho, const double* _
   }
 }
 
+// ---- vector operations of the explicit driver loop: the stage
+// combinations and the weighted RMS norm ARKODE evaluates through N_VLinearCombination /
+// N_VWrmsNorm on the MPIManyVector.  One pass each, HBM bound, grid-stride over a grid that
+// is a multiple of the SM count.
+struct LinCombArgs {
+  int nterms;
+  double c[8];
+  const double* x[8];
+};
+__global__ void lincomb_kernel(const LinCombArgs a, double* __restrict__ out, long n)
+{
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    double s = a.c[0] * a.x[0][i];
+#pragma unroll 1
+    for (int t = 1; t < a.nterms; t++) s = fma(a.c[t], a.x[t][i], s);
+    out[i] = s;
+  }
+}
+// sum_i (x_i / (rtol*|y_i| + atol))^2  accumulated into *acc (one atomicAdd per CTA)
+__global__ void wrms_kernel(const double* __restrict__ x, const double* __restrict__ y, double rtol, double atol,
+                            long n, double* __restrict__ acc)
+{
+  double s = 0.0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double q = x[i] / fma(rtol, fabs(y[i]), atol);
+    s = fma(q, q, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double part[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) part[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    s = (lane < (blockDim.x >> 5)) ? part[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(acc, s);
+  }
+}
+
 // DFMA throughput micro-benchmark: 8 independent dependency chains per thread.  Used by
 // bench.py for the FP64-pipe roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b)
@@ -746,6 +787,31 @@ int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl
   for (int f = 0; f < 5; f++)
     EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f], w[f], sizeof(double) * N, cudaMemcpyHostToDevice, c->s_cmp));
   return eulerb200_stability(c, c->stage_w, cfl, dt_stab, c->s_cmp);
+}
+
+int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x,
+                          double* out, int64_t n, void* stream)
+{
+  if (!c || !coef || !x || !out || nterms < 1 || nterms > 8) return -1;
+  LinCombArgs a;
+  a.nterms = nterms;
+  for (int t = 0; t < nterms; t++) { a.c[t] = coef[t]; a.x[t] = x[t]; }
+  const unsigned blocks = (unsigned)std::min<long>((n + 255) / 256, 148L * 16);
+  lincomb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out, n);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int eulerb200_vec_wrms_accum(eulerb200_ctx* c, const double* x, const double* y, double rtol, double atol,
+                             int64_t n, double* acc, void* stream)
+{
+  if (!c || !x || !y || !acc) return -1;
+  const unsigned blocks = (unsigned)std::min<long>((n + 255) / 256, 148L * 8);
+  wrms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, rtol, atol, n, acc);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
 }
 
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }

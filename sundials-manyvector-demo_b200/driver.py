@@ -1,0 +1,229 @@
+"""Explicit time-stepping driver with device-resident stage vectors.
+
+Stands in for what ``euler3D_main.cpp:191-417`` asks of ARKODE's ARKStep in the explicit
+runs of the reference (sod, linear_advection, rayleigh_taylor, hurricane, fluid_blast):
+
+* embedded explicit Runge-Kutta step with the tables ARKODE uses by default for
+  ``order`` 2/3/4 (Heun-Euler 2-1-2, Bogacki-Shampine 4-2-3, Zonneveld 5-3-4),
+* WRMS error norm with scalar tolerances (``ARKStepSStolerances``), PID step controller
+  with ARKODE's default constants, error-test failures, optional fixed step,
+* the CFL hook (``ARKStepSetStabilityFn(stability)``, used when ``cfl > 0``),
+* stop times / output cadence and the final counters (steps, attempts, RHS evals, error
+  test failures) printed at ``euler3D_main.cpp:432-449``.
+
+SUNDIALS is not available in this image, so this is NOT ARKODE: step sequences will differ
+in detail from a reference run (run-level parity is unpinned); what the tests pin
+is that the same loop driven by the CUDA RHS and by the CPU oracle RHS produce the same
+trajectory, and that the reference's analytic diagnostics come out small.
+
+The stage vectors never leave the GPU: stage combinations and the error norm are single
+passes of ``eulerb200_vec_lincomb`` / ``eulerb200_vec_wrms_accum`` over each sub-vector.
+The numerical kernels are behind the ``VecOps`` interface so that tests can run the very
+same loop on numpy arrays with the oracle as right-hand side.
+"""
+import ctypes as C
+import math
+
+# (A rows, b, b_embedded, method order p, embedding order q)
+TABLES = {
+    2: ([[], [1.0]], [0.5, 0.5], [1.0, 0.0], 2, 1),                                    # Heun-Euler 2-1-2
+    3: ([[], [0.5], [0.0, 0.75], [2.0 / 9, 1.0 / 3, 4.0 / 9]],                          # Bogacki-Shampine 4-2-3
+        [2.0 / 9, 1.0 / 3, 4.0 / 9, 0.0], [7.0 / 24, 0.25, 1.0 / 3, 0.125], 3, 2),
+    4: ([[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0], [5.0 / 32, 7.0 / 32, 13.0 / 32, -1.0 / 32]],  # Zonneveld 5-3-4
+        [1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6, 0.0], [-0.5, 7.0 / 3, 7.0 / 3, 13.0 / 6, -16.0 / 3], 4, 3),
+}
+
+
+class ARKODEParameters:
+    """The fields of ``class ARKODEParameters`` (euler3D.hpp:126-172) the explicit runs use."""
+
+    def __init__(self, **kw):
+        self.order = 4
+        self.rtol, self.atol = 1e-8, 1e-12
+        self.fixedstep = 0
+        self.h0 = self.hmin = self.hmax = 0.0
+        self.safety = self.bias = self.growth = 0.0      # 0 => default, as in the input files
+        self.k1 = self.k2 = self.k3 = 0.0
+        self.etamx1 = self.etamxf = 0.0
+        self.maxnef = 0
+        self.mxsteps = 5000
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+class TorchVecOps:
+    """Stage-vector arithmetic on ManyVectors of CUDA tensors through the C ABI."""
+
+    def __init__(self, pkg, udata, process_group=None):
+        import torch
+        self.torch, self.pkg, self.u, self.pg = torch, pkg, udata, process_group
+        self.lib = pkg.load_library()
+        self.acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self.nglobal = udata.nx * udata.ny * udata.nz * (5 + udata.nchem)
+
+    def new_like(self, w):
+        return self.pkg.ManyVector([self.torch.empty_like(s) for s in w.sub])
+
+    def lincomb(self, out, coefs, vecs):
+        """out = sum_t coefs[t] * vecs[t]  (out may be one of vecs)"""
+        stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        n = len(vecs)
+        cf = (C.c_double * n)(*[float(c) for c in coefs])
+        for f in range(len(out.sub)):
+            ptrs = (C.c_void_p * n)(*[v.sub[f].data_ptr() for v in vecs])
+            ret = self.lib.eulerb200_vec_lincomb(self.u._ctx, n, cf, ptrs, C.c_void_p(out.sub[f].data_ptr()),
+                                                 out.sub[f].numel(), stream)
+            if ret != 0:
+                raise self.pkg.EulerB200Error(self.u.last_error())
+
+    def wrms(self, x, y, rtol, atol):
+        """ARKODE's N_VWrmsNorm(x, ewt) with ewt = 1/(rtol |y| + atol), over all ranks."""
+        stream = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        self.acc.zero_()
+        for f in range(len(x.sub)):
+            ret = self.lib.eulerb200_vec_wrms_accum(self.u._ctx, C.c_void_p(x.sub[f].data_ptr()),
+                                                    C.c_void_p(y.sub[f].data_ptr()), rtol, atol,
+                                                    x.sub[f].numel(), C.c_void_p(self.acc.data_ptr()), stream)
+            if ret != 0:
+                raise self.pkg.EulerB200Error(self.u.last_error())
+        if self.u.nprocs > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.acc, group=self.pg)
+        return math.sqrt(float(self.acc.item()) / self.nglobal)
+
+    def rhs(self, t, w, wdot):
+        return self.pkg.fEuler(t, w, wdot, self.u)
+
+    def stability(self, w, t):
+        return self.pkg.stability(w, t, self.u)
+
+
+class ERKStep:
+    """``ARKStepCreate(fEuler, NULL, t0, w, ctx)`` + options + ``ARKStepEvolve`` for the
+    explicit drivers.  ``ops`` supplies the vector arithmetic and the right-hand side."""
+
+    def __init__(self, ops, t0, w, opts=None, cfl=0.0):
+        self.ops, self.t, self.w = ops, float(t0), w
+        self.o = opts or ARKODEParameters()
+        if self.o.order not in TABLES:
+            raise ValueError("explicit tables are provided for order 2, 3 and 4")
+        self.A, self.b, self.bhat, self.p, self.q = TABLES[self.o.order]
+        self.cfl = cfl
+        s = len(self.b)
+        self.k = [ops.new_like(w) for _ in range(s)]
+        self.ytmp, self.yerr = ops.new_like(w), ops.new_like(w)
+        # ARKODE defaults (arkode_adapt: PID controller)
+        self.safety = self.o.safety or 0.96
+        self.bias = self.o.bias or 1.5
+        self.growth = self.o.growth or 20.0
+        self.k1, self.k2, self.k3 = (self.o.k1 or 0.58), (self.o.k2 or 0.21), (self.o.k3 or 0.1)
+        self.etamx1 = self.o.etamx1 or 10000.0
+        self.etamxf = self.o.etamxf or 0.3
+        self.maxnef = self.o.maxnef or 7
+        self.h = 0.0
+        self.ehist = [1.0, 1.0]
+        self.nst = self.nst_a = self.nfe = self.netf = 0
+
+    # -- pieces --------------------------------------------------------------------
+    def _f(self, t, y, out):
+        ret = self.ops.rhs(t, y, out)
+        self.nfe += 1
+        if ret != 0:
+            raise RuntimeError("fEuler failed with flag %d at t = %g" % (ret, t))
+
+    def _initial_step(self, tout):
+        if self.o.fixedstep:
+            return self.o.hmax
+        if self.o.h0 > 0:
+            return self.o.h0
+        o = self.ops
+        # Hairer-Norsett-Wanner starting step on the WRMS norm
+        self._f(self.t, self.w, self.k[0])
+        zero_ref = self.w
+        d0 = o.wrms(self.w, zero_ref, self.o.rtol, self.o.atol)
+        d1 = o.wrms(self.k[0], zero_ref, self.o.rtol, self.o.atol)
+        h0 = 0.01 * d0 / d1 if d0 > 1e-5 and d1 > 1e-5 else 1e-6
+        h0 = min(h0, abs(tout - self.t))
+        o.lincomb(self.ytmp, [1.0, h0], [self.w, self.k[0]])
+        self._f(self.t + h0, self.ytmp, self.k[1])
+        o.lincomb(self.yerr, [1.0, -1.0], [self.k[1], self.k[0]])
+        d2 = o.wrms(self.yerr, zero_ref, self.o.rtol, self.o.atol) / h0
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / (self.p + 1)) if max(d1, d2) > 1e-15 else max(1e-6, 1e-3 * h0)
+        return min(100.0 * h0, h1, abs(tout - self.t))
+
+    def _attempt(self, h):
+        """One embedded RK step of size h from (t, w); returns the scaled error estimate."""
+        o, A = self.ops, self.A
+        s = len(self.b)
+        for i in range(s):
+            if i == 0:
+                self._f(self.t, self.w, self.k[0])
+            else:
+                terms = [(h * A[i][j], self.k[j]) for j in range(i) if A[i][j] != 0.0]
+                o.lincomb(self.ytmp, [1.0] + [c for c, _ in terms], [self.w] + [v for _, v in terms])
+                self._f(self.t + sum(A[i]) * h, self.ytmp, self.k[i])
+        bt = [(h * self.b[j], self.k[j]) for j in range(s) if self.b[j] != 0.0]
+        o.lincomb(self.ytmp, [1.0] + [c for c, _ in bt], [self.w] + [v for _, v in bt])      # new solution
+        if self.o.fixedstep:
+            return 0.0
+        et = [(h * (self.b[j] - self.bhat[j]), self.k[j]) for j in range(s) if self.b[j] != self.bhat[j]]
+        o.lincomb(self.yerr, [c for c, _ in et], [v for _, v in et])
+        return self.bias * o.wrms(self.yerr, self.w, self.o.rtol, self.o.atol)
+
+    def _eta_pid(self, dsm):
+        e1 = max(dsm, 1e-10)
+        e2, e3 = self.ehist
+        kk = self.q + 1                              # ARKODE adapts on the embedding order by default
+        return self.safety * e1 ** (-self.k1 / kk) * e2 ** (self.k2 / kk) * e3 ** (-self.k3 / kk)
+
+    # -- public --------------------------------------------------------------------
+    def evolve(self, tout):
+        """ARKStepEvolve(arkode_mem, tout, w, &t, ARK_NORMAL) with the stop time at tout.
+        Returns (retval, t): 0 on success, -1 on failure (too many steps / error failures)."""
+        tout = float(tout)
+        if self.h == 0.0:
+            self.h = self._initial_step(tout)
+        steps_here = 0
+        while self.t < tout * (1 - 1e-14) - 1e-300:
+            if steps_here >= self.o.mxsteps:
+                return -1, self.t
+            h = self.h
+            if self.o.hmax > 0 and not self.o.fixedstep:
+                h = min(h, self.o.hmax)
+            if self.cfl > 0 and not self.o.fixedstep:
+                ret, dt_stab = self.ops.stability(self.w, self.t)
+                if ret != 0:
+                    return -1, self.t
+                h = min(h, dt_stab)
+            h = min(h, tout - self.t)
+            nef = 0
+            while True:
+                self.nst_a += 1
+                dsm = self._attempt(h)
+                if self.o.fixedstep or dsm <= 1.0:
+                    break
+                self.netf += 1
+                nef += 1
+                if nef >= self.maxnef or h <= max(self.o.hmin, 1e-14 * max(abs(self.t), 1.0)):
+                    return -1, self.t
+                eta = min(self.etamxf if nef >= 2 else 1.0, max(0.1, self._eta_pid(dsm)))
+                h *= eta
+            # accept
+            self.w, self.ytmp = self.ytmp, self.w
+            self.t += h
+            self.nst += 1
+            steps_here += 1
+            if not self.o.fixedstep:
+                eta = self._eta_pid(dsm)
+                eta = min(eta, self.etamx1 if self.nst == 1 else self.growth)
+                if 1.0 < eta < 1.5:                   # ARKODE's "small growth" dead band
+                    eta = 1.0
+                self.ehist = [max(dsm, 1e-10), self.ehist[0]]
+                self.h = max(h * eta, self.o.hmin)
+        self.t = tout
+        return 0, self.t
+
+    def stats(self):
+        return {"nst": self.nst, "nst_a": self.nst_a, "nfe": self.nfe, "netf": self.netf}

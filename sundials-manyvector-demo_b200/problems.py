@@ -1,0 +1,244 @@
+"""Problem plug-ins: the reference links one problem file per
+executable, each providing ``initial_conditions``, ``external_forces`` and
+``output_diagnostics`` (euler3D.hpp:1448-1457).  Here a problem is a name:
+
+    sod_x | sod_y | sod_z                     sod.cpp
+    linear_advection_x | _y | _z              linear_advection.cpp
+    rayleigh_taylor                           rayleigh_taylor.cpp
+    hurricane_xy | hurricane_yz | hurricane_zx    hurricane.cpp
+
+plus the two diagnostics of io.cpp every driver prints: ``check_conservation`` (:504-541)
+and ``print_stats`` (:552-636).  States are built and reduced on the device (torch is the
+array plumbing here; none of this is on the timed path).  The exact Riemann solution used
+by the Sod diagnostics (sod.cpp:214-379) is evaluated on the host per x-location.
+"""
+import math
+
+BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_REFLECTING = 0, 1, 2, 3
+
+
+def _coords(torch, u, device):
+    f64 = dict(dtype=torch.float64, device=device)
+    x = (torch.arange(u.nxl, **f64) + (u.is_ + 0.5)) * u.dx + u.xl
+    y = (torch.arange(u.nyl, **f64) + (u.js + 0.5)) * u.dy + u.yl
+    z = (torch.arange(u.nzl, **f64) + (u.ks + 0.5)) * u.dz + u.zl
+    Z, Y, X = torch.meshgrid(z, y, x, indexing="ij")       # flat index i + nxl*(j + nyl*k)
+    return X.reshape(-1), Y.reshape(-1), Z.reshape(-1)
+
+
+def configure(problem, u):
+    """Domain / boundary conditions / gamma of the shipped input files for `problem`
+    (tests/*/input_*.txt); grid sizes are left to the caller."""
+    if problem.startswith("sod"):
+        u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = BC_NEUMANN
+        u.gamma = 1.4
+    elif problem.startswith("linear_advection"):
+        u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = BC_PERIODIC
+        u.gamma = 1.4
+    elif problem == "rayleigh_taylor":
+        u.xl, u.xr, u.yl, u.yr = -0.25, 0.25, -0.75, 0.75
+        u.xlbc = u.xrbc = BC_PERIODIC
+        u.ylbc = u.yrbc = BC_REFLECTING
+        u.zlbc = u.zrbc = BC_NEUMANN
+        u.gamma = 1.4
+        u.forcing = [0.0, 0.0, -0.1, 0.0, 0.0]            # rayleigh_taylor.cpp:117-128
+    elif problem.startswith("hurricane"):
+        u.xl = u.yl = u.zl = -1.0
+        u.xr = u.yr = u.zr = 1.0
+        u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = BC_NEUMANN
+        u.gamma = 2.0
+    else:
+        raise ValueError("unknown problem %r" % problem)
+
+
+def initial_conditions(problem, t, w, u):
+    """``int initial_conditions(const realtype& t, N_Vector w, const EulerData& udata)``"""
+    import torch
+    dev = w.sub[0].device
+    X, Y, Z = _coords(torch, u, dev)
+    zero = torch.zeros_like(X)
+    mx, my, mz = zero.clone(), zero.clone(), zero.clone()
+    if problem.startswith("sod"):                                   # sod.cpp:50-55,120-160
+        s = {"x": X, "y": Y, "z": Z}[problem[-1]]
+        left = s < 0.5
+        one = torch.ones_like(X)
+        rho = torch.where(left, one, 0.125 * one)
+        p = torch.where(left, one, 0.1 * one)
+    elif problem.startswith("linear_advection"):                    # linear_advection.cpp:51-68,117-131
+        s = {"x": X, "y": Y, "z": Z}[problem[-1]]
+        rho = 1.0 + 0.1 * torch.sin(2.0 * math.pi * (s - 0.5 * t))
+        v = 0.5 * rho
+        mx, my, mz = (v if problem[-1] == "x" else zero, v if problem[-1] == "y" else zero,
+                      v if problem[-1] == "z" else zero)
+        p = torch.ones_like(X)
+    elif problem == "rayleigh_taylor":                              # rayleigh_taylor.cpp:48-53,104-109
+        rho = torch.where(Y > 0.0, 2.0 * torch.ones_like(X), torch.ones_like(X))
+        my = rho * 0.01 * (1.0 + torch.cos(4.0 * math.pi * X)) * (1.0 + torch.cos(3.0 * math.pi * Y))
+        p = 2.5 - 0.1 * rho * Y
+    elif problem.startswith("hurricane"):                           # hurricane.cpp:58-60,120-183
+        a, b = {"xy": (X, Y), "zx": (Z, X), "yz": (Y, Z)}[problem[-2:]]
+        r = torch.sqrt(a * a + b * b)
+        r = torch.where(r == 0.0, torch.full_like(r, 1e-14), r)
+        ma, mb = 10.0 * (b / r), -10.0 * (a / r)
+        if problem[-2:] == "xy":
+            mx, my = ma, mb
+        elif problem[-2:] == "zx":
+            mz, mx = ma, mb
+        else:
+            my, mz = ma, mb
+        rho = torch.ones_like(X)
+        p = torch.full_like(X, 25.0)
+        if u.nchem > 0:                                             # colour stripes in angle
+            theta = torch.atan2(b, a)
+            chem = torch.zeros(X.numel(), u.nchem, dtype=torch.float64, device=dev)
+            for v in range(u.nchem):
+                lo, hi = -math.pi + v * 2 * math.pi / u.nchem, -math.pi + (v + 1) * 2 * math.pi / u.nchem
+                chem[:, v] = ((theta >= lo) & (theta < hi)).to(torch.float64)
+            w.sub[5].copy_(chem.reshape(-1))
+    else:
+        raise ValueError("unknown problem %r" % problem)
+    et = p / (u.gamma - 1.0) + (mx * mx + my * my + mz * mz) * 0.5 / rho       # eos_inv, euler3D.hpp:1393
+    for dst, src in zip(w.sub[:5], (rho, mx, my, mz, et)):
+        dst.copy_(src)
+    if u.nchem > 0 and not problem.startswith("hurricane"):
+        w.sub[5].zero_()
+    return 0
+
+
+# ---- exact Riemann solution of the Sod tube (sod.cpp:214-379), host side ----------------
+def _fsecant(p4, p1, p5, rho1, rho5, g):
+    z = p4 / p5 - 1.0
+    c1, c5 = math.sqrt(g * p1 / rho1), math.sqrt(g * p5 / rho5)
+    fact = (g - 1.0) / (2 * g) * (c5 / c1) * z / math.sqrt(1.0 + (g + 1.0) / (2 * g) * z)
+    return p1 * (1.0 - fact) ** (2 * g / (g - 1.0)) - p4
+
+
+def exact_riemann(t, xs, xI, g, rhoL=1.0, rhoR=0.125, pL=1.0, pR=0.1):
+    """rho, u, p at time t for every x in xs (pL > pR branch, the shipped problem)."""
+    rho1, p1, rho5, p5 = rhoL, pL, rhoR, pR
+    p40, p41 = p1, p5
+    f0 = _fsecant(p40, p1, p5, rho1, rho5, g)
+    p4 = p41
+    for _ in range(50):
+        f1 = _fsecant(p41, p1, p5, rho1, rho5, g)
+        if f1 == f0:
+            break
+        p4 = p41 - (p41 - p40) * f1 / (f1 - f0)
+        if abs(p4 - p41) / abs(p41) < 1e-14:
+            break
+        p40, p41, f0 = p41, p4, f1
+    z = p4 / p5 - 1.0
+    c5 = math.sqrt(g * p5 / rho5)
+    gm1, gp1 = g - 1.0, g + 1.0
+    fact = math.sqrt(1.0 + 0.5 * gp1 * z / g)
+    u4 = c5 * z / (g * fact)
+    rho4 = rho5 * (1.0 + 0.5 * gp1 * z / g) / (1.0 + 0.5 * gm1 * z / g)
+    wsh = c5 * fact
+    p3, u3 = p4, u4
+    rho3 = rho1 * (p3 / p1) ** (1.0 / g)
+    c1, c3 = math.sqrt(g * p1 / rho1), math.sqrt(g * p3 / rho3)
+    xsh, xcd, xft, xhd = xI + wsh * t, xI + u3 * t, xI + (u3 - c3) * t, xI - c1 * t
+    out = []
+    for x in xs:
+        if x < xhd:
+            out.append((rho1, 0.0, p1))
+        elif x < xft:
+            u = 2.0 / gp1 * (c1 + (x - xI) / t)
+            f = 1.0 - 0.5 * gm1 * u / c1
+            out.append((rho1 * f ** (2.0 / gm1), u, p1 * f ** (2.0 * g / gm1)))
+        elif x < xcd:
+            out.append((rho3, u3, p3))
+        elif x < xsh:
+            out.append((rho4, u4, p4))
+        else:
+            out.append((rho5, 0.0, p5))
+    return out
+
+
+def _true_state(problem, t, u, dev):
+    import torch
+    X, Y, Z = _coords(torch, u, dev)
+    zero = torch.zeros_like(X)
+    if problem.startswith("linear_advection"):
+        s = {"x": X, "y": Y, "z": Z}[problem[-1]]
+        rho = 1.0 + 0.1 * torch.sin(2.0 * math.pi * (s - 0.5 * t))
+        v = 0.5 * rho
+        m = [v if problem[-1] == a else zero for a in "xyz"]
+        et = 1.0 / (u.gamma - 1.0) + (m[0] ** 2 + m[1] ** 2 + m[2] ** 2) * 0.5 / rho
+        return [rho] + m + [et]
+    if problem.startswith("sod"):
+        ax = problem[-1]
+        n1 = {"x": u.nxl, "y": u.nyl, "z": u.nzl}[ax]
+        o1 = {"x": u.is_, "y": u.js, "z": u.ks}[ax]
+        d1 = {"x": u.dx, "y": u.dy, "z": u.dz}[ax]
+        l1 = {"x": u.xl, "y": u.yl, "z": u.zl}[ax]
+        xs = [(o1 + q + 0.5) * d1 + l1 for q in range(n1)]
+        sol = exact_riemann(t, xs, 0.5, u.gamma) if t > 0 else [((1.0, 0.0, 1.0) if x < 0.5 else (0.125, 0.0, 0.1)) for x in xs]
+        tab = torch.tensor(sol, dtype=torch.float64, device=dev)              # [n1, 3]
+        idx = torch.arange(u.nxl * u.nyl * u.nzl, device=dev)
+        q = {"x": idx % u.nxl, "y": (idx // u.nxl) % u.nyl, "z": idx // (u.nxl * u.nyl)}[ax]
+        rho, vel, p = tab[q, 0], tab[q, 1], tab[q, 2]
+        m = [rho * vel if ax == a else zero for a in "xyz"]
+        et = p / (u.gamma - 1.0) + (m[0] ** 2 + m[1] ** 2 + m[2] ** 2) * 0.5 / rho
+        return [rho] + m + [et]
+    return None
+
+
+def _allreduce(t, op, u, group):
+    if u.nprocs > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op), group=group)
+    return t
+
+
+def output_diagnostics(problem, t, w, u, group=None, quiet=False):
+    """``output_diagnostics``: errI (max) and errR (RMS) of the five fluid fields against the
+    analytic solution (linear_advection.cpp:168-240, sod.cpp:383-467); None for problems whose
+    reference hook prints nothing."""
+    import torch
+    true = _true_state(problem, t, u, w.sub[0].device)
+    if true is None:
+        return None
+    errI = torch.stack([(a - b).abs().max() for a, b in zip(true, w.sub[:5])])
+    errR = torch.stack([((a - b) ** 2).sum() for a, b in zip(true, w.sub[:5])])
+    errI = _allreduce(errI, "MAX", u, group).cpu().tolist()
+    errR = torch.sqrt(_allreduce(errR, "SUM", u, group) / (u.nx * u.ny * u.nz)).cpu().tolist()
+    if u.myid == 0 and not quiet:
+        print("     errI = " + "  ".join("%9.2e" % e for e in errI))
+        print("     errR = " + "  ".join("%9.2e" % e for e in errR))
+    return {"errI": errI, "errR": errR}
+
+
+class Conservation:
+    """``check_conservation`` (io.cpp:504-541): total mass and energy, then relative drift."""
+
+    def __init__(self):
+        self.saved = None
+
+    def __call__(self, t, w, u, group=None, quiet=False):
+        import torch
+        tot = torch.stack([w.sub[0].sum(), w.sub[4].sum()]) * (u.dx * u.dy * u.dz)
+        tot = _allreduce(tot, "SUM", u, group).cpu().tolist()
+        if self.saved is None:
+            self.saved = tot
+            if u.myid == 0 and not quiet:
+                print("   Total mass   = %.16e\n   Total energy = %.16e" % tuple(tot))
+            return {"mass": tot[0], "energy": tot[1]}
+        drift = [abs(tot[i] - self.saved[i]) / self.saved[i] for i in range(2)]
+        if u.myid == 0 and not quiet:
+            print("   Mass conservation relative change   = %7.2e" % drift[0])
+            print("   Energy conservation relative change = %7.2e" % drift[1])
+        return {"mass": tot[0], "energy": tot[1], "mass_drift": drift[0], "energy_drift": drift[1]}
+
+
+def print_stats(t, w, u, nst, group=None, quiet=False):
+    """``print_stats`` (io.cpp:552-636): RMS of every field over the global grid."""
+    import torch
+    sq = [(s * s).sum() for s in w.sub[:5]]
+    if u.nchem > 0:
+        sq += list((w.sub[5].view(-1, u.nchem) ** 2).sum(0))
+    tot = _allreduce(torch.stack(sq), "SUM", u, group)
+    rms = torch.sqrt(tot / (u.nx * u.ny * u.nz)).cpu().tolist()
+    if u.myid == 0 and not quiet:
+        print("  %9.1e " % t + " ".join("%9.1e" % r for r in rms) + "  %6d" % nst)
+    return rms

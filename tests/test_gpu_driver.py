@@ -1,0 +1,125 @@
+"""GPU tier for the widened rows: the explicit driver loop
+with device-resident stage vectors, the problem plug-ins and the run diagnostics.
+Run-level parity: the SAME ERKStep loop is driven once by the CUDA right-hand side (stage
+arithmetic through eulerb200_vec_lincomb / _wrms_accum) and once by the CPU oracle with numpy
+arithmetic; step sequences and final states must agree."""
+import numpy as np
+import pytest
+
+from helpers import NpVec, OracleVecOps, make_udata
+
+pytestmark = pytest.mark.gpu
+P, N, D, R = 0, 1, 2, 3
+
+
+def setup(pkg, problem, n, nchem=0):
+    import torch
+    u = pkg.EulerData(nchem=nchem)
+    u.nx, u.ny, u.nz = n
+    pkg.problems.configure(problem, u)
+    assert u.SetupDecomp(device=0) == 0
+    w = pkg.ManyVector.new(u)
+    assert pkg.problems.initial_conditions(problem, 0.0, w, u) == 0
+    torch.cuda.synchronize()
+    return u, w
+
+
+@pytest.mark.parametrize("problem,n,tf,opts", [
+    ("sod_x", (64, 3, 3), 0.05, dict(order=4, fixedstep=1, hmax=0.002)),
+    ("linear_advection_y", (3, 24, 3), 0.1, dict(order=3, fixedstep=1, hmax=0.005)),
+    ("rayleigh_taylor", (12, 36, 3), 0.05, dict(order=4, fixedstep=1, hmax=0.005)),
+    ("hurricane_yz", (3, 20, 20), 0.01, dict(order=2, fixedstep=1, hmax=0.001)),
+])
+def test_cuda_run_equals_oracle_run_fixed_step(pkg, port, problem, n, tf, opts):
+    """Fixed step: the two trajectories are the same arithmetic up to RHS rounding, so the
+    final states agree to ~1e-12 after tens of steps."""
+    u, w = setup(pkg, problem, n)
+    gpu = pkg.driver.ERKStep(pkg.driver.TorchVecOps(pkg, u), 0.0, w, pkg.driver.ARKODEParameters(**opts))
+    parts = [s.cpu().numpy().copy() for s in w.sub]
+    ops = OracleVecOps(port, None, n, 0, (u.dx, u.dy, u.dz), u.gamma, u.bcs, forcing=u.forcing)
+    cpu = pkg.driver.ERKStep(ops, 0.0, NpVec(parts), pkg.driver.ARKODEParameters(**opts))
+    r1, t1 = gpu.evolve(tf)
+    r2, t2 = cpu.evolve(tf)
+    assert r1 == 0 and r2 == 0 and t1 == t2 == tf
+    assert gpu.stats() == cpu.stats()
+    mom = max(np.abs(b).max() for b in cpu.w.sub[1:4])
+    for f, (a, b) in enumerate(zip(gpu.w.sub, cpu.w.sub)):
+        scale = mom if f in (1, 2, 3) else np.abs(b).max()
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-11 * max(scale, 1e-30)
+    u.FreeData()
+
+
+def test_cuda_run_vs_oracle_run_adaptive(pkg, port):
+    """Adaptive stepping on a shock problem amplifies 1e-15 RHS differences through the
+    accept/reject decisions, so step sequences need not match; the solutions still agree to
+    the integration tolerance and the work is comparable."""
+    n, tf = (64, 3, 3), 0.05
+    opts = dict(order=4, rtol=1e-5, atol=1e-12)
+    u, w = setup(pkg, "sod_x", n)
+    gpu = pkg.driver.ERKStep(pkg.driver.TorchVecOps(pkg, u), 0.0, w, pkg.driver.ARKODEParameters(**opts))
+    parts = [s.cpu().numpy().copy() for s in w.sub]
+    ops = OracleVecOps(port, None, n, 0, (u.dx, u.dy, u.dz), u.gamma, u.bcs)
+    cpu = pkg.driver.ERKStep(ops, 0.0, NpVec(parts), pkg.driver.ARKODEParameters(**opts))
+    assert gpu.evolve(tf)[0] == 0 and cpu.evolve(tf)[0] == 0
+    assert abs(gpu.stats()["nst"] - cpu.stats()["nst"]) <= 0.15 * cpu.stats()["nst"]
+    for a, b in zip(gpu.w.sub[:1] + gpu.w.sub[4:5], cpu.w.sub[:1] + cpu.w.sub[4:5]):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-4 * np.abs(b).max()
+    u.FreeData()
+
+
+def test_sod_x_full_run_diagnostics(pkg):
+    """inputs/input_sod.txt: 200x3x3, all-Neumann, tf = 0.2, order 4, rtol 1e-5, atol 1e-12,
+    10 outputs.  The reference prints errI/errR per output and the conservation drift; here
+    they are asserted: RMS density error below 2e-2 at every output (first order at the shock), transverse momenta
+    exactly zero."""
+    u, w = setup(pkg, "sod_x", (200, 3, 3))
+    step = pkg.driver.ERKStep(pkg.driver.TorchVecOps(pkg, u), 0.0, w,
+                              pkg.driver.ARKODEParameters(order=4, rtol=1e-5, atol=1e-12, mxsteps=10000))
+    cons = pkg.problems.Conservation()
+    cons(0.0, w, u, quiet=True)
+    for iout in range(10):
+        ret, t = step.evolve(0.02 * (iout + 1))
+        assert ret == 0
+        diag = pkg.problems.output_diagnostics("sod_x", t, step.w, u, quiet=True)
+        assert diag["errR"][0] < 2e-2 and diag["errI"][2] == 0.0 and diag["errI"][3] == 0.0
+        rms = pkg.problems.print_stats(t, step.w, u, step.nst, quiet=True)
+        assert len(rms) == 5 and rms[2] == 0.0
+    st = step.stats()
+    assert st["nst"] > 20 and st["nfe"] >= 5 * st["nst"]
+    c = cons(t, step.w, u, quiet=True)
+    assert c["mass_drift"] < 1e-12         # waves have not reached the Neumann ends at t = 0.2
+    u.FreeData()
+
+
+def test_linear_advection_3d_conservation_and_error(pkg):
+    """linear_advection_x on a genuinely 3-D periodic grid: analytic error small, mass and
+    energy conserved to round-off (check_conservation, io.cpp:504-541)."""
+    u, w = setup(pkg, "linear_advection_x", (48, 12, 10))
+    step = pkg.driver.ERKStep(pkg.driver.TorchVecOps(pkg, u), 0.0, w,
+                              pkg.driver.ARKODEParameters(order=4, rtol=1e-8, atol=1e-12))
+    cons = pkg.problems.Conservation()
+    cons(0.0, w, u, quiet=True)
+    ret, t = step.evolve(0.5)
+    assert ret == 0
+    diag = pkg.problems.output_diagnostics("linear_advection_x", t, step.w, u, quiet=True)
+    assert diag["errI"][0] < 5e-6 and diag["errR"][4] < 5e-6
+    c = cons(t, step.w, u, quiet=True)
+    assert c["mass_drift"] < 1e-13 and c["energy_drift"] < 1e-13
+    u.FreeData()
+
+
+def test_initial_conditions_match_reference_closed_forms(pkg):
+    """Device initial conditions == the closed forms of the problem files (restated in numpy
+    by tests/golden/make_golden.py, which also fed them to the reference)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+    for problem, kind, n, box, gamma in (("sod_x", "sod", (40, 3, 3), (0, 1, 0, 1, 0, 1), 1.4),
+                                         ("rayleigh_taylor", "rayleigh_taylor", (8, 12, 3), (-0.25, 0.25, -0.75, 0.75, 0, 1), 1.4),
+                                         ("hurricane_yz", "hurricane", (3, 16, 16), (-1, 1, -1, 1, -1, 1), 2.0),
+                                         ("linear_advection_y", "advection_y", (6, 16, 5), (0, 1, 0, 1, 0, 1), 1.4)):
+        u, w = setup(pkg, problem, n)
+        want = mg.make_state(kind, n, 0, box, gamma, seed=0)
+        for a, b in zip(w.sub, want[:5]):
+            assert np.abs(a.cpu().numpy() - b).max() <= 1e-13 * max(1.0, np.abs(b).max())
+        u.FreeData()
