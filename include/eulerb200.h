@@ -101,6 +101,15 @@ int eulerb200_rhs_async(eulerb200_ctx* ctx, double t, const double* const* w, do
                         void* stream);
 int eulerb200_state_flag(eulerb200_ctx* ctx, void* stream, int32_t* bits);
 
+/* fslow / fexpl of the multirate and IMEX drivers, fused (multirate_chem_hydro_main.cpp:
+ * 996-1083, imex_chem_hydro_main.cpp:910-1000): rebuild the total energy from the gas energy
+ * carried as the last chemistry species, et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho) -- written
+ * into w[4] like the reference does -- evaluate fEuler, then chemdot[nchem-1] = etdot and
+ * etdot = 0.  The Dengo scaling of chem before/after stays with the chemistry side.  Device
+ * pointers; synchronous on the legal_state flag like eulerb200_rhs. */
+int eulerb200_rhs_slow(eulerb200_ctx* ctx, double t, double* const* w, double* const* wdot,
+                       double energy_units, void* stream);
+
 /* Same call with HOST arrays (what a driver holding serial N_Vectors has): stages
  * host->device, evaluates, stages device->host, pipelined over z-slabs. */
 int eulerb200_rhs_host(eulerb200_ctx* ctx, double t, const double* const* w_host,

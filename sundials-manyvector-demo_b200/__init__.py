@@ -57,6 +57,7 @@ ABI = {
     "eulerb200_rhs": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_rhs_async": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_state_flag": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "eulerb200_rhs_slow": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_double, C.c_void_p]),
     "eulerb200_rhs_host": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6]),
     "eulerb200_rhs_any": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_exchange_start": (C.c_int, [C.c_void_p, _vp6, C.c_void_p]),
@@ -319,6 +320,17 @@ def fEuler(t, w, wdot, user_data, sync=True):
         fn = lib.eulerb200_rhs if sync else lib.eulerb200_rhs_async
         return fn(u._ctx, float(t), w.pointers(), wdot.pointers(), u._stream())
     return lib.eulerb200_rhs_host(u._ctx, float(t), w.pointers(), wdot.pointers())
+
+
+def fslow(t, w, wdot, user_data):
+    """``fslow`` (multirate_chem_hydro_main.cpp:996-1083) / ``fexpl`` (imex_chem_hydro_main.cpp:
+    910-1000) without the Dengo scaling: total energy rebuilt from the gas energy species,
+    fEuler, ``chemdot[nchem-1] = etdot``, ``etdot = 0`` -- one fused call, no host copies of
+    the chemistry vector.  ``user_data.EnergyUnits`` as in euler3D.hpp:233.  Mutates ``w``'s et."""
+    lib = load_library()
+    u = user_data
+    return lib.eulerb200_rhs_slow(u._ctx, float(t), w.pointers(), wdot.pointers(),
+                                  float(getattr(u, "EnergyUnits", 1.0)), u._stream())
 
 
 def stability(w, t, user_data):

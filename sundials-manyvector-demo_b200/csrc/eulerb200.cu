@@ -317,6 +317,9 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
     eb::ghost_face(g, f, c->recv[f], &P.ghost[f]);
   }
   for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
+  P.slow_mode = 0;
+  P.inv_energy_units = 1.0;
+  P.et_rw = nullptr;
   P.state_flag = c->d_flag;
   P.lo[0] = P.lo[1] = P.lo[2] = 0;
   P.hi[0] = P.nx; P.hi[1] = P.ny; P.hi[2] = P.nz;
@@ -347,7 +350,7 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
 // Per-cell derived values for the z-planes [k0, k1) of the state in P.
 int launch_aux(eulerb200_ctx* c, const eb::RhsParams& P, long k0, long k1, cudaStream_t s)
 {
-  if (!c->use_aux || k1 <= k0) return 0;
+  if ((!c->use_aux && !P.slow_mode) || k1 <= k0) return 0;
   const long plane = P.nx * P.ny, c0 = k0 * plane, c1 = k1 * plane;
   const unsigned blocks = (unsigned)std::min<long>((c1 - c0 + 255) / 256, 148L * 16);
   eb::aux_kernel<<<blocks, 256, 0, s>>>(P, c->aux[0], c->aux[1], c->aux[2], c->aux[3], c0, c1);
@@ -595,15 +598,49 @@ int eulerb200_ghost_face(eulerb200_ctx* c, const double* const* w, int32_t f, do
   return 0;
 }
 
+static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdot, void* stream,
+                    int slow_mode, double energy_units);
+
 int eulerb200_rhs_async(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* stream)
 {
   (void)t;   // every shipped forcing is time independent
+  return rhs_impl(c, w, wdot, stream, 0, 1.0);
+}
+
+int eulerb200_rhs_slow(eulerb200_ctx* c, double t, double* const* w, double* const* wdot, double energy_units,
+                       void* stream)
+{
+  (void)t;
+  if (!c) return -1;
+  if (c->cfg.nchem < 1) return fail(c, -1, "slow RHS needs the gas energy as the last chemistry species (nchem >= 1)");
+  if (!(energy_units > 0)) return fail(c, -1, "EnergyUnits must be positive (euler3D.hpp:385-393)");
+  int rc = rhs_impl(c, w, wdot, stream, 1, energy_units);
+  if (rc) return rc;
+  int32_t bits = 0;
+  rc = eulerb200_state_flag(c, stream, &bits);
+  if (rc) return rc;
+  if (bits) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
+    return fail(c, -1, msg);
+  }
+  return 0;
+}
+
+static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdot, void* stream,
+                    int slow_mode, double energy_units)
+{
   if (!c || !w || !wdot) return -1;
   for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++)
     if (!w[f] || !wdot[f]) return fail(c, -1, "NULL sub-vector pointer (utilities.cpp:31-58)");
   cudaStream_t s = (cudaStream_t)stream;
   EB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), s));
-  const eb::RhsParams P = make_params(c, w, wdot);
+  eb::RhsParams P = make_params(c, w, wdot);
+  if (slow_mode) {
+    P.slow_mode = 1;
+    P.inv_energy_units = 1.0 / energy_units;
+    P.et_rw = const_cast<double*>(w[4]);
+  }
   const long n[3] = {P.nx, P.ny, P.nz};
   {
     int rc_ = launch_aux(c, P, 0, P.nz, s);

@@ -55,6 +55,14 @@ struct RhsParams {
   const double* aux[4];     // per-cell 1/rho, p, c, sqrt(rho) from aux_kernel (or all NULL:
                             // everything derived on the fly)
   int* state_flag;          // OR of legal_state failure bits (euler3D.hpp:1405-1414)
+  // "slow RHS" mode of the multirate / IMEX drivers (fslow, multirate_chem_hydro_main.cpp:
+  // 996-1083; fexpl, imex_chem_hydro_main.cpp:910-1000): before the fluxes the total energy is
+  // rebuilt from the gas energy carried as the LAST chemistry species,
+  //   et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho)            (:1033-1042, written into w)
+  // and afterwards  chemdot[nchem-1] = etdot,  etdot = 0        (:1059-1068).
+  int slow_mode;
+  double inv_energy_units;
+  double* et_rw;            // w[4] again, writable, for the rebuild (slow mode only)
   // sub-box of cells to evaluate: [lo, hi) per axis (the whole box for a single launch;
   // interior / boundary shells when the halo exchange is overlapped)
   long lo[3], hi[3];
@@ -241,8 +249,16 @@ EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, l
 __global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2, double* a3, long c0, long c1)
 {
   for (long c = c0 + (long)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (long)gridDim.x * blockDim.x) {
-    const CellAux a = cell_aux(P.gamma, P.w[0][c], P.w[1][c], P.w[2][c], P.w[3][c], P.w[4][c]);
-    a0[c] = a.rinv; a1[c] = a.p; a2[c] = a.c; a3[c] = a.sr;
+    const double r = P.w[0][c], mx = P.w[1][c], my = P.w[2][c], mz = P.w[3][c];
+    double e = P.w[4][c];
+    if (P.slow_mode) {
+      e = P.w[5][c * P.nchem + (P.nchem - 1)] * P.inv_energy_units + 0.5 / r * (mx * mx + my * my + mz * mz);
+      P.et_rw[c] = e;
+    }
+    if (a0 != nullptr) {
+      const CellAux a = cell_aux(P.gamma, r, mx, my, mz, e);
+      a0[c] = a.rinv; a1[c] = a.p; a2[c] = a.c; a3[c] = a.sr;
+    }
   }
 }
 
@@ -302,8 +318,17 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)
                                         + (zup - ZLO[v * T]) * P.rdz;
                       ZLO[v * T] = zup;
-                      if (v < 5) P.wdot[v][cell] = P.forcing[v] - div;
-                      else P.wdot[5][cell * P.nchem + (v - 5)] = 0.0 - div;
+                      if (!P.slow_mode) {
+                        if (v < 5) P.wdot[v][cell] = P.forcing[v] - div;
+                        else P.wdot[5][cell * P.nchem + (v - 5)] = 0.0 - div;
+                      } else if (v == 4) {          // etdot goes to the gas-energy species
+                        P.wdot[5][cell * P.nchem + (P.nchem - 1)] = P.forcing[4] - div;
+                        P.wdot[4][cell] = 0.0;
+                      } else if (v < 4) {
+                        P.wdot[v][cell] = P.forcing[v] - div;
+                      } else if (v < 4 + P.nchem) {  // every species but the last (overwritten above)
+                        P.wdot[5][cell * P.nchem + (v - 5)] = 0.0 - div;
+                      }
                     });
     }
     __syncthreads();

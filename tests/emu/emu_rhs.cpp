@@ -21,6 +21,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   for (int f = 0; f < 6; f++)
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
   for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
+  P.slow_mode = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
   if (use_aux) {
     const long N = P.nx * P.ny * P.nz;
     for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);

@@ -123,3 +123,34 @@ def test_initial_conditions_match_reference_closed_forms(pkg):
         for a, b in zip(w.sub, want[:5]):
             assert np.abs(a.cpu().numpy() - b).max() <= 1e-13 * max(1.0, np.abs(b).max())
         u.FreeData()
+
+
+@pytest.mark.parametrize("n,nchem,bcs,eu", [((24, 20, 16), 4, [P] * 6, 1.0), ((33, 12, 9), 10, [R] * 6, 3.7e3)])
+def test_fslow_fused_matches_reference_sequence(pkg, oracle_mod, port, n, nchem, bcs, eu):
+    """eulerb200_rhs_slow == the reference's fslow sequence
+    (multirate_chem_hydro_main.cpp:1033-1068) applied around the ORACLE fEuler:
+    et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho); fEuler; chemdot[nchem-1] = etdot; etdot = 0."""
+    import torch
+    from conftest import normwise_errors, rounding_floor
+    u = make_udata(pkg, n, nchem, bcs, forcing=[0, 0, -0.1, 0, 0])
+    u.EnergyUnits = eu
+    parts = oracle_mod.random_state(n, nchem, seed=3)
+    chem = parts[5].reshape(-1, nchem)
+    chem[:, -1] = eu * (2.0 + np.random.default_rng(1).random(chem.shape[0]))       # gas energy, CGS-like
+    parts[4][:] = -1.0                                                               # must be rebuilt, not read
+    w = pkg.ManyVector([torch.from_numpy(p).cuda() for p in parts])
+    wdot = pkg.ManyVector.new(u)
+    assert pkg.fslow(0.0, w, wdot, u) == 0, u.last_error()
+    ref_parts = [p.copy() for p in parts]
+    ref_parts[4] = chem[:, -1] * (1.0 / eu) + 0.5 / parts[0] * (parts[1] ** 2 + parts[2] ** 2 + parts[3] ** 2)
+    assert np.abs(w.sub[4].cpu().numpy() - ref_parts[4]).max() <= 1e-15 * np.abs(ref_parts[4]).max()
+    ret, ref, _ = port.feuler(port.cfg(n, nchem, (u.dx, u.dy, u.dz), u.gamma, bcs, forcing=u.forcing), ref_parts)
+    assert ret == 0
+    ref[5].reshape(-1, nchem)[:, -1] = ref[4]
+    ref[4] = np.zeros_like(ref[4])
+    got = [s.cpu().numpy() for s in wdot.sub]
+    assert np.all(got[4] == 0.0)
+    floor = rounding_floor(ref_parts, u.gamma, (u.dx, u.dy, u.dz))
+    floor[4] = 0.0
+    assert max(normwise_errors(got, ref, floor)) <= 1e-12
+    u.FreeData()
