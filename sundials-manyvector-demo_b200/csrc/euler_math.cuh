@@ -33,6 +33,12 @@
 #define EB_HD inline
 #endif
 
+#ifdef EB_WENO_ONE_NEWTON
+#define EB_WENO_RCP fast_rcp1
+#else
+#define EB_WENO_RCP fast_rcp
+#endif
+
 namespace eb {
 
 // SUNRsqrt of SUNDIALS 6.2 (sundials_math.h): x <= 0 gives 0.
@@ -40,6 +46,20 @@ EB_HD double sun_sqrt(double x) { return (x <= 0.0) ? 0.0 : sqrt(x); }
 
 // Reciprocal on the FP64 pipe: hardware seed + two Newton steps (about 1 ulp); the
 // full IEEE division sequence costs roughly twice as many FP64 issue slots.
+// One Newton step only (relative error ~1e-14): enough where the reciprocal multiplies a
+// correction term that is itself O(differences between the candidate stencils), as in weno5.
+EB_HD double fast_rcp1(double b)
+{
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  const double e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / b;
+#endif
+}
+
 EB_HD double fast_rcp(double b)
 {
 #if defined(__CUDA_ARCH__)
@@ -79,7 +99,7 @@ EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
   const double den = fma(0.3, P1, fma(0.6, P2, 0.1 * P3));
   const double num = fma((0.1 / 3.0) * P3, D3 - D2, (-0.3 / 6.0) * P1 * (D1 - D2));
   const double q2 = fma(1.0 / 3.0, v3, fma(5.0 / 6.0, v2, (-1.0 / 6.0) * v1));
-  return fma(num, fast_rcp(den), q2);
+  return fma(num, EB_WENO_RCP(den), q2);
 }
 
 // Roe-averaged face state and the projection coefficients derived from it.
