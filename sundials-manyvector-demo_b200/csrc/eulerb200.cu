@@ -256,7 +256,7 @@ struct eulerb200_ctx {
   double* stage_w[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* stage_wdot[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
-  static const int kMaxSlabs = 16;
+  static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
   size_t max_smem_set = 0;
@@ -735,6 +735,7 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
     // A slab can be evaluated once the slab above it is resident (3-plane stencil reach);
     // with a periodic wrap in z the first slab also needs the last one, so it goes last.
     int S = (int)std::min<long>(eulerb200_ctx::kMaxSlabs, std::max<long>(1, g.nzl / 8));
+    if (const char* ev = getenv("EULERB200_HOST_SLABS")) S = std::max(1, std::min(S, atoi(ev)));
     long zb[eulerb200_ctx::kMaxSlabs + 1];
     for (int s = 0; s <= S; s++) zb[s] = g.nzl * s / S;
     EB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_cmp));
