@@ -150,6 +150,18 @@ int eulerb200_vec_lincomb(eulerb200_ctx* ctx, int32_t nterms, const double* coef
 int eulerb200_vec_wrms_accum(eulerb200_ctx* ctx, const double* x, const double* y, double rtol, double atol,
                              int64_t n, double* acc, void* stream);
 
+/* N_VWrmsNorm over the whole ManyVector and all ranks (nglobal = global vector length);
+ * synchronous, result on the host. */
+int eulerb200_vec_wrms(eulerb200_ctx* ctx, const double* const* x, const double* const* y, double rtol,
+                       double atol, int64_t nglobal, double* result, void* stream);
+
+/* Device-memory helpers so that a C/C++ host driver needs no CUDA headers
+ * (N_VNew_* / N_VDestroy and the host<->device copies of a device-vector build). */
+void* eulerb200_device_alloc(int64_t bytes);
+void eulerb200_device_free(void* p);
+int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes);
+int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes);
+
 /* Number of kernel launches issued through this context so far. */
 int64_t eulerb200_launch_count(const eulerb200_ctx* ctx);
 

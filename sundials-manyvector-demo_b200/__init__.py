@@ -70,6 +70,12 @@ ABI = {
                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "eulerb200_vec_wrms_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                           C.c_int64, C.c_void_p, C.c_void_p]),
+    "eulerb200_vec_wrms": (C.c_int, [C.c_void_p, _vp6, _vp6, C.c_double, C.c_double, C.c_int64,
+                                    C.POINTER(C.c_double), C.c_void_p]),
+    "eulerb200_device_alloc": (C.c_void_p, [C.c_int64]),
+    "eulerb200_device_free": (None, [C.c_void_p]),
+    "eulerb200_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "eulerb200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),
     "eulerb200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }

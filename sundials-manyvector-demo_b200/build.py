@@ -46,5 +46,22 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+DRIVER = os.path.join(HERE, "euler3d_b200")
+
+
+def build_driver(force=False):
+    """The native explicit driver (host/euler3d_b200.cpp): plain C++ on top of the C ABI."""
+    src = os.path.join(HERE, "host", "euler3d_b200.cpp")
+    if not force and os.path.exists(DRIVER) and os.path.getmtime(DRIVER) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return DRIVER
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(HERE, "..", "include"), "-o", DRIVER, src,
+           "-L", HERE, "-leulerb200", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building euler3d_b200")
+    return DRIVER
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))

@@ -11,6 +11,7 @@
 // ---------------------------------------------------------------------------
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <math.h>
 #include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -850,6 +851,44 @@ int eulerb200_vec_wrms_accum(eulerb200_ctx* c, const double* x, const double* y,
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
+}
+
+// ||x||_WRMS over the whole ManyVector and all ranks: sqrt( sum (x_i/(rtol|y_i|+atol))^2 / nglobal )
+int eulerb200_vec_wrms(eulerb200_ctx* c, const double* const* x, const double* const* y, double rtol, double atol,
+                       int64_t nglobal, double* result, void* stream)
+{
+  if (!c || !x || !y || !result || nglobal <= 0) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* acc = reinterpret_cast<double*>(c->d_alpha);      // 8-byte device scratch shared with stability()
+  EB_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double), s));
+  const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
+  for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++) {
+    int rc = eulerb200_vec_wrms_accum(c, x[f], y[f], rtol, atol, f < 5 ? N : N * c->cfg.nchem, acc, stream);
+    if (rc) return rc;
+  }
+  if (c->cfg.nranks > 1 && c->comm)
+    EB_NCCL(c, nccl().AllReduce(acc, acc, 1, ncclDouble, ncclSum, c->comm, s));
+  EB_CUDA(c, cudaMemcpyAsync(c->h_alpha, acc, sizeof(double), cudaMemcpyDeviceToHost, s));
+  EB_CUDA(c, cudaStreamSynchronize(s));
+  *result = sqrt(*c->h_alpha / (double)nglobal);
+  return 0;
+}
+
+// Plain device-memory helpers so that a C/C++ host driver needs no CUDA headers.
+void* eulerb200_device_alloc(int64_t bytes)
+{
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void eulerb200_device_free(void* p) { if (p) cudaFree(p); }
+int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes)
+{
+  return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : fail(nullptr, -2, "cudaMemcpy H2D failed");
+}
+int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes)
+{
+  return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : fail(nullptr, -2, "cudaMemcpy D2H failed");
 }
 
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }

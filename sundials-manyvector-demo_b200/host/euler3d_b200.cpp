@@ -1,0 +1,442 @@
+// ---------------------------------------------------------------------------
+// euler3d_b200.cpp -- native explicit driver for the B200 fluid RHS (SURVEY.md 8(f-1), 8(f-2),
+// 8(f-4)).  Plays the part of src/euler3D_main.cpp for the explicit problems of the
+// reference when SUNDIALS is not available: same input files ("key = value" lines and
+// --key=value overrides, io.cpp:225-367), same run structure (initial outputs, nout
+// evolve/diagnostics cycles, final statistics and conservation check,
+// euler3D_main.cpp:300-462), same diagnostics text (errI / errR, stats table, conservation).
+//
+//   euler3d_b200 --problem=sod_x -f input_sod.txt [--nx=400 --rtol=1e-6 ...]
+//
+// Problems (chosen at link time in the reference, by name here): sod_{x,y,z},
+// linear_advection_{x,y,z}, rayleigh_taylor, hurricane_{xy,yz,zx}.
+// The state lives on the GPU for the whole run; this file contains no CUDA: device memory,
+// the right-hand side, the stage combinations and the error norm all go through the C ABI
+// of include/eulerb200.h.  The time integrator is the embedded explicit Runge-Kutta loop
+// described in driver.py (ARKODE's default tables and controller constants; it is not
+// ARKODE).  One rank.
+// ---------------------------------------------------------------------------
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+#include "eulerb200.h"
+
+namespace {
+
+const double PI = 3.14159265358979323846;
+
+struct Inputs {
+  std::map<std::string, double> v;
+  std::string problem = "sod_x";
+  double get(const std::string& k, double dflt) const { auto it = v.find(k); return it == v.end() ? dflt : it->second; }
+};
+
+bool parse_line(const std::string& line, Inputs& in)
+{
+  std::string s = line.substr(0, line.find('#'));
+  const size_t eq = s.find('=');
+  if (eq == std::string::npos) return false;
+  auto trim = [](std::string t) {
+    const size_t a = t.find_first_not_of(" \t\r\n"), b = t.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
+  };
+  const std::string key = trim(s.substr(0, eq)), val = trim(s.substr(eq + 1));
+  if (key.empty() || val.empty()) return false;
+  if (key == "problem") { in.problem = val; return true; }
+  char* end = nullptr;
+  const double x = strtod(val.c_str(), &end);
+  if (end == val.c_str()) return false;
+  in.v[key] = x;
+  return true;
+}
+
+struct Vec {                       // the MPIManyVector composition: 5 fluid sub-vectors (+ chem)
+  double* sub[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  long len[6] = {0, 0, 0, 0, 0, 0};
+  int nsub = 5;
+};
+
+Vec new_vec(long N, int nchem)
+{
+  Vec v;
+  v.nsub = 5 + (nchem > 0 ? 1 : 0);
+  for (int f = 0; f < v.nsub; f++) {
+    v.len[f] = f < 5 ? N : N * nchem;
+    v.sub[f] = (double*)eulerb200_device_alloc(sizeof(double) * v.len[f]);
+    if (!v.sub[f]) { fprintf(stderr, "MEMORY_ERROR: device allocation failed\n"); exit(1); }
+  }
+  return v;
+}
+void free_vec(Vec& v) { for (int f = 0; f < v.nsub; f++) eulerb200_device_free(v.sub[f]); }
+
+struct Problem {
+  std::string name;
+  long nx, ny, nz;
+  double xl, xr, yl, yr, zl, zr, gamma;
+  double dx() const { return (xr - xl) / nx; }
+  double dy() const { return (yr - yl) / ny; }
+  double dz() const { return (zr - zl) / nz; }
+  char axis() const { return name[name.size() - 1]; }
+};
+
+// exact Riemann solution of the Sod tube (sod.cpp:214-379; pL > pR branch)
+double fsecant(double p4, double p1, double p5, double rho1, double rho5, double g)
+{
+  const double z = p4 / p5 - 1.0, c1 = sqrt(g * p1 / rho1), c5 = sqrt(g * p5 / rho5);
+  const double fact = (g - 1.0) / (2 * g) * (c5 / c1) * z / sqrt(1.0 + (g + 1.0) / (2 * g) * z);
+  return p1 * pow(1.0 - fact, 2 * g / (g - 1.0)) - p4;
+}
+void exact_riemann(double t, double x, double xI, double g, double& rho, double& u, double& p)
+{
+  const double rho1 = 1.0, p1 = 1.0, rho5 = 0.125, p5 = 0.1;
+  double p40 = p1, p41 = p5, f0 = fsecant(p40, p1, p5, rho1, rho5, g), p4 = p41;
+  for (int it = 0; it < 50; it++) {
+    const double f1 = fsecant(p41, p1, p5, rho1, rho5, g);
+    if (f1 == f0) break;
+    p4 = p41 - (p41 - p40) * f1 / (f1 - f0);
+    if (fabs(p4 - p41) / fabs(p41) < 1e-14) break;
+    p40 = p41; p41 = p4; f0 = f1;
+  }
+  const double z = p4 / p5 - 1.0, c5 = sqrt(g * p5 / rho5), gm1 = g - 1.0, gp1 = g + 1.0;
+  const double fact = sqrt(1.0 + 0.5 * gp1 * z / g);
+  const double u4 = c5 * z / (g * fact), rho4 = rho5 * (1.0 + 0.5 * gp1 * z / g) / (1.0 + 0.5 * gm1 * z / g);
+  const double w = c5 * fact, p3 = p4, u3 = u4, rho3 = rho1 * pow(p3 / p1, 1.0 / g);
+  const double c1 = sqrt(g * p1 / rho1), c3 = sqrt(g * p3 / rho3);
+  const double xsh = xI + w * t, xcd = xI + u3 * t, xft = xI + (u3 - c3) * t, xhd = xI - c1 * t;
+  if (x < xhd) { rho = rho1; p = p1; u = 0.0; }
+  else if (x < xft) {
+    u = 2.0 / gp1 * (c1 + (x - xI) / t);
+    const double f = 1.0 - 0.5 * gm1 * u / c1;
+    rho = rho1 * pow(f, 2.0 / gm1); p = p1 * pow(f, 2.0 * g / gm1);
+  }
+  else if (x < xcd) { rho = rho3; p = p3; u = u3; }
+  else if (x < xsh) { rho = rho4; p = p4; u = u4; }
+  else { rho = rho5; p = p5; u = 0.0; }
+}
+
+// Analytic / initial state of cell (i,j,k) at time t; returns false if the problem has no
+// analytic solution for t > 0 (then only t = t0 is meaningful).
+bool state_at(const Problem& P, double t, long i, long j, long k, double w[5])
+{
+  const double x = (i + 0.5) * P.dx() + P.xl, y = (j + 0.5) * P.dy() + P.yl, z = (k + 0.5) * P.dz() + P.zl;
+  double rho = 1.0, m[3] = {0, 0, 0}, p = 1.0;
+  bool analytic = true;
+  if (P.name.compare(0, 3, "sod") == 0) {
+    const int a = P.axis() - 'x';
+    const double s = a == 0 ? x : (a == 1 ? y : z);
+    double u = 0.0;
+    if (t > 0.0) exact_riemann(t, s, 0.5, P.gamma, rho, u, p);
+    else { rho = s < 0.5 ? 1.0 : 0.125; p = s < 0.5 ? 1.0 : 0.1; }
+    m[a] = rho * u;
+  } else if (P.name.compare(0, 16, "linear_advection") == 0) {
+    const int a = P.axis() - 'x';
+    const double s = a == 0 ? x : (a == 1 ? y : z);
+    rho = 1.0 + 0.1 * sin(2.0 * PI * (s - 0.5 * t));
+    m[a] = 0.5 * rho;
+  } else if (P.name == "rayleigh_taylor") {
+    rho = y > 0.0 ? 2.0 : 1.0;
+    m[1] = rho * 0.01 * (1.0 + cos(4.0 * PI * x)) * (1.0 + cos(3.0 * PI * y));
+    p = 2.5 - 0.1 * rho * y;
+    analytic = false;
+  } else if (P.name.compare(0, 9, "hurricane") == 0) {
+    const std::string pl = P.name.substr(P.name.size() - 2);
+    const double a = pl == "xy" ? x : (pl == "zx" ? z : y), b = pl == "xy" ? y : (pl == "zx" ? x : z);
+    double r = sqrt(a * a + b * b);
+    if (r == 0.0) r = 1e-14;
+    const double ma = 10.0 * (b / r), mb = -10.0 * (a / r);
+    if (pl == "xy") { m[0] = ma; m[1] = mb; } else if (pl == "zx") { m[2] = ma; m[0] = mb; } else { m[1] = ma; m[2] = mb; }
+    p = 25.0;
+    analytic = false;
+  } else {
+    fprintf(stderr, "unknown problem '%s'\n", P.name.c_str());
+    exit(1);
+  }
+  w[0] = rho; w[1] = m[0]; w[2] = m[1]; w[3] = m[2];
+  w[4] = p / (P.gamma - 1.0) + (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) * 0.5 / rho;      // eos_inv
+  return analytic;
+}
+
+// embedded explicit Runge-Kutta tables: ARKODE's defaults for order 2, 3, 4
+struct Table { int s, p, q; double A[5][5], b[5], bh[5]; };
+Table make_table(int order)
+{
+  Table T;
+  memset(&T, 0, sizeof T);
+  if (order == 2) { T.s = 2; T.p = 2; T.q = 1; T.A[1][0] = 1.0; T.b[0] = T.b[1] = 0.5; T.bh[0] = 1.0; }
+  else if (order == 3) {
+    T.s = 4; T.p = 3; T.q = 2;
+    T.A[1][0] = 0.5; T.A[2][1] = 0.75; T.A[3][0] = 2.0 / 9; T.A[3][1] = 1.0 / 3; T.A[3][2] = 4.0 / 9;
+    T.b[0] = 2.0 / 9; T.b[1] = 1.0 / 3; T.b[2] = 4.0 / 9;
+    T.bh[0] = 7.0 / 24; T.bh[1] = 0.25; T.bh[2] = 1.0 / 3; T.bh[3] = 0.125;
+  } else {
+    T.s = 5; T.p = 4; T.q = 3;
+    T.A[1][0] = 0.5; T.A[2][1] = 0.5; T.A[3][2] = 1.0;
+    T.A[4][0] = 5.0 / 32; T.A[4][1] = 7.0 / 32; T.A[4][2] = 13.0 / 32; T.A[4][3] = -1.0 / 32;
+    T.b[0] = 1.0 / 6; T.b[1] = 1.0 / 3; T.b[2] = 1.0 / 3; T.b[3] = 1.0 / 6;
+    T.bh[0] = -0.5; T.bh[1] = 7.0 / 3; T.bh[2] = 7.0 / 3; T.bh[3] = 13.0 / 6; T.bh[4] = -16.0 / 3;
+  }
+  return T;
+}
+
+struct Stepper {
+  eulerb200_ctx* ctx;
+  Table T;
+  Vec w, ytmp, yerr, k[5];
+  long nglobal;
+  double t = 0, h = 0, rtol, atol, hmin = 0, hmax = 0, h0 = 0, cfl = 0;
+  int fixedstep = 0, mxsteps = 5000, maxnef = 7;
+  double safety = 0.96, bias = 1.5, growth = 20.0, k1 = 0.58, k2 = 0.21, k3 = 0.1, etamx1 = 1e4, etamxf = 0.3;
+  double e2 = 1.0, e3 = 1.0;
+  long nst = 0, nst_a = 0, nfe = 0, netf = 0;
+
+  void die(const char* what) { fprintf(stderr, "\n%s: %s\n\n", what, eulerb200_last_error(ctx)); exit(1); }
+  void lincomb(Vec& out, int n, const double* c, Vec* const* v)
+  {
+    for (int f = 0; f < out.nsub; f++) {
+      const double* x[8];
+      for (int q = 0; q < n; q++) x[q] = v[q]->sub[f];
+      if (eulerb200_vec_lincomb(ctx, n, c, x, out.sub[f], out.len[f], NULL)) die("eulerb200_vec_lincomb");
+    }
+  }
+  double wrms(const Vec& x, const Vec& y)
+  {
+    double r = 0;
+    if (eulerb200_vec_wrms(ctx, x.sub, y.sub, rtol, atol, nglobal, &r, NULL)) die("eulerb200_vec_wrms");
+    return r;
+  }
+  void f(double tt, Vec& y, Vec& out)
+  {
+    nfe++;
+    if (eulerb200_rhs(ctx, tt, y.sub, out.sub, NULL)) die("fEuler");
+  }
+  double initial_step(double tout)
+  {
+    if (fixedstep) return hmax;
+    if (h0 > 0) return h0;
+    f(t, w, k[0]);
+    const double d0 = wrms(w, w), d1 = wrms(k[0], w);
+    double hh = (d0 > 1e-5 && d1 > 1e-5) ? 0.01 * d0 / d1 : 1e-6;
+    hh = std::min(hh, fabs(tout - t));
+    { const double c[2] = {1.0, hh}; Vec* v[2] = {&w, &k[0]}; lincomb(ytmp, 2, c, v); }
+    f(t + hh, ytmp, k[1]);
+    { const double c[2] = {1.0, -1.0}; Vec* v[2] = {&k[1], &k[0]}; lincomb(yerr, 2, c, v); }
+    const double d2 = wrms(yerr, w) / hh, dm = std::max(d1, d2);
+    const double h1 = dm > 1e-15 ? pow(0.01 / dm, 1.0 / (T.p + 1)) : std::max(1e-6, 1e-3 * hh);
+    return std::min(std::min(100.0 * hh, h1), fabs(tout - t));
+  }
+  double attempt(double hh)
+  {
+    for (int i = 0; i < T.s; i++) {
+      if (i == 0) { f(t, w, k[0]); continue; }
+      double c[8]; Vec* v[8]; int n = 0; double ci = 0;
+      c[n] = 1.0; v[n++] = &w;
+      for (int j = 0; j < i; j++) { ci += T.A[i][j]; if (T.A[i][j] != 0.0) { c[n] = hh * T.A[i][j]; v[n++] = &k[j]; } }
+      lincomb(ytmp, n, c, v);
+      f(t + ci * hh, ytmp, k[i]);
+    }
+    { double c[8]; Vec* v[8]; int n = 0; c[n] = 1.0; v[n++] = &w;
+      for (int j = 0; j < T.s; j++) if (T.b[j] != 0.0) { c[n] = hh * T.b[j]; v[n++] = &k[j]; }
+      lincomb(ytmp, n, c, v); }
+    if (fixedstep) return 0.0;
+    { double c[8]; Vec* v[8]; int n = 0;
+      for (int j = 0; j < T.s; j++) if (T.b[j] != T.bh[j]) { c[n] = hh * (T.b[j] - T.bh[j]); v[n++] = &k[j]; }
+      lincomb(yerr, n, c, v); }
+    return bias * wrms(yerr, w);
+  }
+  double eta_pid(double dsm) const
+  {
+    const double e1 = std::max(dsm, 1e-10), kk = T.q + 1;
+    return safety * pow(e1, -k1 / kk) * pow(e2, k2 / kk) * pow(e3, -k3 / kk);
+  }
+  int evolve(double tout)
+  {
+    if (h == 0.0) h = initial_step(tout);
+    long steps = 0;
+    while (t < tout * (1 - 1e-14) - 1e-300) {
+      if (steps >= mxsteps) return -1;
+      double hh = h;
+      if (hmax > 0 && !fixedstep) hh = std::min(hh, hmax);
+      if (cfl > 0 && !fixedstep) {
+        double dt = 0;
+        if (eulerb200_stability(ctx, w.sub, cfl, &dt, NULL)) die("stability");
+        hh = std::min(hh, dt);
+      }
+      hh = std::min(hh, tout - t);
+      int nef = 0;
+      double dsm = 0;
+      for (;;) {
+        nst_a++;
+        dsm = attempt(hh);
+        if (fixedstep || dsm <= 1.0) break;
+        netf++; nef++;
+        if (nef >= maxnef || hh <= std::max(hmin, 1e-14 * std::max(fabs(t), 1.0))) return -1;
+        hh *= std::min(nef >= 2 ? etamxf : 1.0, std::max(0.1, eta_pid(dsm)));
+      }
+      std::swap(w, ytmp);
+      t += hh; nst++; steps++;
+      if (!fixedstep) {
+        double eta = std::min(eta_pid(dsm), nst == 1 ? etamx1 : growth);
+        if (eta > 1.0 && eta < 1.5) eta = 1.0;
+        e3 = e2; e2 = std::max(dsm, 1e-10);
+        h = std::max(hh * eta, hmin);
+      }
+    }
+    t = tout;
+    return 0;
+  }
+};
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+  Inputs in;
+  std::vector<std::string> overrides;
+  for (int a = 1; a < argc; a++) {
+    const std::string s = argv[a];
+    if (s == "-f" && a + 1 < argc) {
+      std::ifstream fin(argv[++a]);
+      if (!fin) { fprintf(stderr, "cannot open input file %s\n", argv[a]); return 1; }
+      std::string line;
+      while (std::getline(fin, line)) parse_line(line, in);
+    } else if (s.compare(0, 2, "--") == 0) overrides.push_back(s.substr(2));
+  }
+  for (const auto& o : overrides) parse_line(o, in);          // command line wins (io.cpp:310-367)
+
+  Problem P;
+  P.name = in.problem;
+  P.nx = (long)in.get("nx", 3); P.ny = (long)in.get("ny", 3); P.nz = (long)in.get("nz", 3);
+  P.xl = in.get("xl", 0); P.xr = in.get("xr", 1); P.yl = in.get("yl", 0); P.yr = in.get("yr", 1);
+  P.zl = in.get("zl", 0); P.zr = in.get("zr", 1);
+  P.gamma = in.get("gamma", 1.4);
+  const double t0 = in.get("t0", 0.0), tf = in.get("tf", 1.0);
+  const int nout = (int)in.get("nout", 10), showstats = (int)in.get("showstats", 0);
+
+  eulerb200_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.nxl = P.nx; cfg.nyl = P.ny; cfg.nzl = P.nz;
+  cfg.nchem = 0; cfg.device = -1;
+  cfg.dx = P.dx(); cfg.dy = P.dy(); cfg.dz = P.dz();
+  cfg.gamma = P.gamma;
+  const char* bcn[6] = {"xlbc", "xrbc", "ylbc", "yrbc", "zlbc", "zrbc"};
+  for (int f = 0; f < 6; f++) {
+    cfg.bc[f] = (int)in.get(bcn[f], 0);
+    cfg.nbr[f] = cfg.bc[f] == EULERB200_BC_PERIODIC ? 0 : EULERB200_NO_NEIGHBOR;
+  }
+  cfg.rank = 0; cfg.nranks = 1;
+  if (P.name == "rayleigh_taylor") cfg.forcing[2] = -0.1;     // rayleigh_taylor.cpp:117-128
+  eulerb200_ctx* ctx = NULL;
+  if (eulerb200_create(&cfg, &ctx) != 0) {
+    fprintf(stderr, "\neulerb200_create failed: %s\n\n", eulerb200_last_error(NULL));
+    return 1;
+  }
+
+  printf("\n3D compressible inviscid Euler test problem (B200 fluid RHS): %s\n", P.name.c_str());
+  printf("   spatial domain: [%g, %g] x [%g, %g] x [%g, %g]\n", P.xl, P.xr, P.yl, P.yr, P.zl, P.zr);
+  printf("   time domain = (%g, %g]\n", t0, tf);
+  printf("   bdry cond (0=per, 1=Neu, 2=Dir, 3=refl): [%d, %d] x [%d, %d] x [%d, %d]\n",
+         cfg.bc[0], cfg.bc[1], cfg.bc[2], cfg.bc[3], cfg.bc[4], cfg.bc[5]);
+  printf("   gamma: %g\n   spatial grid: %ld x %ld x %ld\n", P.gamma, P.nx, P.ny, P.nz);
+
+  const long N = P.nx * P.ny * P.nz;
+  Stepper S;
+  S.ctx = ctx;
+  S.T = make_table((int)in.get("order", 4));
+  S.nglobal = 5 * N;
+  S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
+  S.fixedstep = (int)in.get("fixedstep", 0);
+  S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
+  S.cfl = in.get("cfl", 0);
+  S.mxsteps = (int)in.get("mxsteps", 5000);
+  auto dflt = [&](const char* k, double d) { const double x = in.get(k, 0); return x != 0 ? x : d; };
+  S.safety = dflt("safety", 0.96); S.bias = dflt("bias", 1.5); S.growth = dflt("growth", 20.0);
+  S.k1 = dflt("k1", 0.58); S.k2 = dflt("k2", 0.21); S.k3 = dflt("k3", 0.1);
+  S.etamx1 = dflt("etamx1", 1e4); S.etamxf = dflt("etamxf", 0.3);
+  S.maxnef = (int)dflt("maxnef", 7);
+  S.t = t0;
+  S.w = new_vec(N, 0); S.ytmp = new_vec(N, 0); S.yerr = new_vec(N, 0);
+  for (int i = 0; i < S.T.s; i++) S.k[i] = new_vec(N, 0);
+
+  // initial conditions (host, then one copy to the device)
+  std::vector<std::vector<double>> host(5, std::vector<double>(N));
+  bool analytic = true;
+  for (long k = 0; k < P.nz; k++)
+    for (long j = 0; j < P.ny; j++)
+      for (long i = 0; i < P.nx; i++) {
+        double w5[5];
+        analytic = state_at(P, t0, i, j, k, w5);
+        const long c = i + P.nx * (j + P.ny * k);
+        for (int f = 0; f < 5; f++) host[f][c] = w5[f];
+      }
+  for (int f = 0; f < 5; f++) eulerb200_copy_to_device(S.w.sub[f], host[f].data(), sizeof(double) * N);
+
+  double mass0 = -1, energy0 = -1;
+  auto outputs = [&](double t, int firstlast) {
+    for (int f = 0; f < 5; f++) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N);
+    if (analytic) {                                           // output_diagnostics of the problem file
+      double errI[5] = {0, 0, 0, 0, 0}, errR[5] = {0, 0, 0, 0, 0};
+      for (long k = 0; k < P.nz; k++)
+        for (long j = 0; j < P.ny; j++)
+          for (long i = 0; i < P.nx; i++) {
+            double w5[5];
+            state_at(P, t, i, j, k, w5);
+            const long c = i + P.nx * (j + P.ny * k);
+            for (int f = 0; f < 5; f++) {
+              const double e = fabs(w5[f] - host[f][c]);
+              errI[f] = std::max(errI[f], e); errR[f] += e * e;
+            }
+          }
+      printf("     errI = %9.2e  %9.2e  %9.2e  %9.2e  %9.2e\n", errI[0], errI[1], errI[2], errI[3], errI[4]);
+      printf("     errR = %9.2e  %9.2e  %9.2e  %9.2e  %9.2e\n", sqrt(errR[0] / N), sqrt(errR[1] / N),
+             sqrt(errR[2] / N), sqrt(errR[3] / N), sqrt(errR[4] / N));
+    }
+    if (showstats) {                                          // print_stats, io.cpp:552-636
+      double rms[5];
+      for (int f = 0; f < 5; f++) { double s = 0; for (long c = 0; c < N; c++) s += host[f][c] * host[f][c]; rms[f] = sqrt(s / N); }
+      if (firstlast == 0) printf("\n      t       ||rho||   ||mx||    ||my||    ||mz||    ||et||      nst\n");
+      printf("  %9.1e %9.1e %9.1e %9.1e %9.1e %9.1e  %6ld\n", t, rms[0], rms[1], rms[2], rms[3], rms[4], S.nst);
+    }
+  };
+  auto conservation = [&]() {                                 // check_conservation, io.cpp:504-541
+    for (int f = 0; f < 5; f += 4) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N);
+    double m = 0, e = 0;
+    for (long c = 0; c < N; c++) { m += host[0][c]; e += host[4][c]; }
+    const double vol = P.dx() * P.dy() * P.dz();
+    m *= vol; e *= vol;
+    if (mass0 == -1) { printf("   Total mass   = %.16e\n   Total energy = %.16e\n", m, e); mass0 = m; energy0 = e; }
+    else {
+      printf("   Mass conservation relative change   = %7.2e\n", fabs(m - mass0) / mass0);
+      printf("   Energy conservation relative change = %7.2e\n", fabs(e - energy0) / energy0);
+    }
+  };
+
+  printf("\nWriting initial batch of outputs\n");
+  if (showstats) conservation();
+  outputs(t0, 0);
+
+  const double dTout = (tf - t0) / nout;
+  double tout = t0 + dTout;
+  for (int iout = 0; iout < nout; iout++) {
+    if (S.evolve(tout) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
+    outputs(S.t, 1);
+    tout = std::min(tout + dTout, tf);
+  }
+
+  printf("\nFinal Solver Statistics:\n");
+  printf("   Internal solver steps = %ld (attempted = %ld)\n", S.nst, S.nst_a);
+  printf("   Total RHS evals:  Fe = %ld,  Fi = 0\n", S.nfe);
+  printf("   Total number of error test failures = %ld\n", S.netf);
+  printf("   GPU kernel launches = %lld\n", (long long)eulerb200_launch_count(ctx));
+  if (showstats) { printf("\nConservation Check:\n"); conservation(); }
+
+  free_vec(S.w); free_vec(S.ytmp); free_vec(S.yerr);
+  for (int i = 0; i < S.T.s; i++) free_vec(S.k[i]);
+  eulerb200_destroy(ctx);
+  return 0;
+}
