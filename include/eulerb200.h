@@ -89,6 +89,17 @@ const char* eulerb200_last_error(const eulerb200_ctx* ctx);   /* ctx may be NULL
 int eulerb200_comm_unique_id(void* id_bytes);
 int eulerb200_comm_attach(eulerb200_ctx* ctx, const void* id_bytes);
 
+/* Peer-store halo transport (one node, CUDA IPC over NVLink/NVSwitch), preferred over the
+ * NCCL send/recv pairs when every neighbour is peer-accessible: the pack kernel of
+ * ExchangeStart writes the three layers straight into the neighbour's ghost slab and
+ * publishes a sequence number there; ExchangeEnd is a one-warp kernel that acquires it.
+ * Every rank exports a blob, the host all-gathers the blobs in rank order (MPI_Allgather in
+ * the drop-in, torch.distributed in the tests) and every rank attaches.  On failure (no
+ * peer access) the context keeps using NCCL. */
+#define EULERB200_P2P_BLOB_BYTES 256
+int eulerb200_p2p_export(eulerb200_ctx* ctx, void* blob_bytes);
+int eulerb200_p2p_attach(eulerb200_ctx* ctx, const void* all_blobs /* nranks blobs */);
+
 /* fEuler (utilities.cpp:17-253): wdot = G - div F(w), including the halo exchange when
  * the context has neighbours.  Enqueued on `stream` (a cudaStream_t, NULL = default).
  * eulerb200_rhs returns only after the legal_state flag has been read back, like the

@@ -54,6 +54,8 @@ ABI = {
     "eulerb200_last_error": (C.c_char_p, [C.c_void_p]),
     "eulerb200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "eulerb200_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eulerb200_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eulerb200_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eulerb200_rhs": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_rhs_async": (C.c_int, [C.c_void_p, C.c_double, _vp6, _vp6, C.c_void_p]),
     "eulerb200_state_flag": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
@@ -255,6 +257,27 @@ class EulerData:
         dist.broadcast(t, src=0, group=process_group)
         raw = bytes(t.cpu().numpy().tobytes())
         self._check(lib.eulerb200_comm_attach(self._ctx, C.create_string_buffer(raw, 128)), self._ctx)
+        # peer-store halo transport (CUDA IPC) unless EULERB200_HALO=nccl; every rank must agree
+        self.halo_transport = "nccl"
+        if os.environ.get("EULERB200_HALO", "p2p") != "nccl":
+            blob = (C.c_char * 256)()
+            ok = lib.eulerb200_p2p_export(self._ctx, blob) == 0
+            mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).clone()
+            if dist.get_backend(process_group) == "nccl":
+                mine = mine.cuda()
+            allb = [torch.empty_like(mine) for _ in range(self.nprocs)]
+            dist.all_gather(allb, mine, group=process_group)
+            rawall = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allb)
+            ok = ok and lib.eulerb200_p2p_attach(self._ctx, C.create_string_buffer(rawall, len(rawall))) == 0
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+            if dist.get_backend(process_group) == "nccl":
+                flag = flag.cuda()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+            if int(flag.item()) == 1:
+                self.halo_transport = "p2p"
+            else:
+                raise EulerB200Error("peer-store halo transport unavailable on some rank (%s); "
+                                     "set EULERB200_HALO=nccl" % lib.eulerb200_last_error(self._ctx).decode())
 
     def _check(self, ret, ctx):
         if ret != 0:

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #define EB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #include "host_setup.h"
@@ -175,6 +176,32 @@ __global__ void wavespeed_kernel(const double* __restrict__ rho, const double* _
   }
 }
 
+// ---- peer-store halo exchange (transport (b)): the pack kernel writes the
+// three layers straight into the NEIGHBOUR's ghost slab over NVLink (CUDA IPC mapping of the
+// neighbour's mailbox); a release store of the exchange's sequence number into the neighbour's
+// arrival word follows in stream order, and the receiver's boundary kernels are preceded by a
+// one-warp kernel that acquires it.  No host involvement, no staging buffer, no side stream.
+__global__ void halo_signal_kernel(unsigned long long* peer_arrival, unsigned long long seq)
+{
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_arrival), "l"(seq) : "memory");
+}
+__global__ void halo_wait_kernel(const unsigned long long* arrival, unsigned mask, unsigned long long seq,
+                                 long long timeout_cycles, int* err)
+{
+  const int f = threadIdx.x;
+  if (f < 6 && ((mask >> f) & 1u)) {
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(arrival + f) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > timeout_cycles) { atomicOr(err, 8); break; }
+      __nanosleep(200);
+    } while (true);
+  }
+}
+
 // ---- vector operations of the explicit driver loop: the stage
 // combinations and the weighted RMS norm ARKODE evaluates through N_VLinearCombination /
 // N_VWrmsNorm on the MPIManyVector.  One pass each, HBM bound, grid-stride over a grid that
@@ -248,6 +275,17 @@ struct eulerb200_ctx {
   bool any_remote = false;
   double* send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double* recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // peer-store halo exchange (CUDA IPC): my mailbox = 2 parities x 6 ghost slabs + 6 arrival words
+  bool p2p = false;
+  char* mailbox = nullptr;
+  int64_t slab_off[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};   // byte offsets inside the mailbox
+  int64_t arrival_off = 0;
+  char* peer_base[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t peer_slab_off[6][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};   // neighbour's slab for MY face f
+  int64_t peer_arrival_off[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<void*> opened;
+  unsigned long long seq = 0;
+  const double* recv_cur[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   ncclComm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
@@ -315,7 +353,7 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   for (int f = 0; f < 6; f++) {
     P.w[f] = (f < 5 || g.nchem > 0) ? w[f] : nullptr;
     P.wdot[f] = (f < 5 || g.nchem > 0) ? wdot[f] : nullptr;
-    eb::ghost_face(g, f, c->recv[f], &P.ghost[f]);
+    eb::ghost_face(g, f, c->recv_cur[f], &P.ghost[f]);
   }
   for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
   P.slow_mode = 0;
@@ -372,8 +410,26 @@ FaceGeom face_geom(const eulerb200_ctx* c, int f, const double* const* w)
 int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
 {
   if (!c->any_remote) return 0;
-  if (!c->comm) return fail(c, -3, "context has remote neighbours but eulerb200_comm_attach was not called");
   const int nv = 5 + c->cfg.nchem;
+  if (c->p2p) {
+    // pack straight into the neighbours' ghost slabs (parity = exchange number mod 2: the slab a
+    // neighbour may still be reading belongs to the previous exchange), then publish the number
+    c->seq++;
+    const int par = (int)(c->seq & 1ull);
+    for (int f = 0; f < 6; f++) {
+      if (!c->remote[f]) continue;
+      const long nent = eb::face_len(c->cfg, f) / nv;
+      double* dst = reinterpret_cast<double*>(c->peer_base[f] + c->peer_slab_off[f][par]);
+      pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), dst, nent);
+      halo_signal_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
+      c->launches += 2;
+      c->recv_cur[f] = reinterpret_cast<const double*>(c->mailbox + c->slab_off[par][f]);
+    }
+    EB_CUDA(c, cudaGetLastError());
+    c->exchange_open = true;
+    return 0;
+  }
+  if (!c->comm) return fail(c, -3, "context has remote neighbours but neither eulerb200_comm_attach nor eulerb200_p2p_attach was called");
   for (int f = 0; f < 6; f++) {
     if (!c->remote[f]) continue;
     const long nent = eb::face_len(c->cfg, f) / nv;
@@ -401,7 +457,16 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
 int exchange_end(eulerb200_ctx* c, cudaStream_t s)
 {
   if (!c->exchange_open) return 0;
-  EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_recv, 0));
+  if (c->p2p) {
+    unsigned mask = 0;
+    for (int f = 0; f < 6; f++) if (c->remote[f]) mask |= 1u << f;
+    halo_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(c->mailbox + c->arrival_off), mask,
+                                      c->seq, 20000000000LL /* ~10 s */, c->d_flag);
+    c->launches++;
+    EB_CUDA(c, cudaGetLastError());
+  } else {
+    EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_recv, 0));
+  }
   c->exchange_open = false;
   return 0;
 }
@@ -508,6 +573,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
       c->any_remote = true;
       EB_CREATE(cudaMalloc(&c->send[f], sizeof(double) * eb::face_len(*cfg, f)));
       EB_CREATE(cudaMalloc(&c->recv[f], sizeof(double) * eb::face_len(*cfg, f)));
+      c->recv_cur[f] = c->recv[f];
     }
   }
   if (c->any_remote) {
@@ -525,6 +591,8 @@ int eulerb200_destroy(eulerb200_ctx* c)
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (void* p : c->opened) cudaIpcCloseMemHandle(p);
+  if (c->mailbox) cudaFree(c->mailbox);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   for (int f = 0; f < 6; f++) {
     if (c->send[f]) cudaFree(c->send[f]);
@@ -570,6 +638,78 @@ int eulerb200_comm_attach(eulerb200_ctx* c, const void* id_bytes)
   return 0;
 }
 
+// Blob a rank publishes: its IPC handle, where each ghost slab sits in its mailbox, and where
+// the arrival words are.
+struct P2PBlob {
+  cudaIpcMemHandle_t handle;                 // 64 bytes
+  int64_t slab_off[2][6];
+  int64_t arrival_off;
+  int64_t face_len[6];
+  int32_t rank, valid;
+  char pad[EULERB200_P2P_BLOB_BYTES - 64 - 96 - 8 - 48 - 8];
+};
+static_assert(sizeof(P2PBlob) == EULERB200_P2P_BLOB_BYTES, "blob size");
+
+int eulerb200_p2p_export(eulerb200_ctx* c, void* blob_bytes)
+{
+  if (!c || !blob_bytes) return -1;
+  EB_CUDA(c, cudaSetDevice(c->device));
+  P2PBlob b;
+  memset(&b, 0, sizeof b);
+  b.rank = c->cfg.rank;
+  if (!c->mailbox) {
+    int64_t off = 0;
+    for (int par = 0; par < 2; par++)
+      for (int f = 0; f < 6; f++) {
+        c->slab_off[par][f] = off;
+        if (c->remote[f]) off += ((int64_t)sizeof(double) * eb::face_len(c->cfg, f) + 255) / 256 * 256;
+      }
+    c->arrival_off = off;
+    off += 256;
+    EB_CUDA(c, cudaMalloc(&c->mailbox, (size_t)off));
+    EB_CUDA(c, cudaMemset(c->mailbox, 0, (size_t)off));
+  }
+  EB_CUDA(c, cudaIpcGetMemHandle(&b.handle, c->mailbox));
+  memcpy(b.slab_off, c->slab_off, sizeof b.slab_off);
+  b.arrival_off = c->arrival_off;
+  for (int f = 0; f < 6; f++) b.face_len[f] = c->remote[f] ? eb::face_len(c->cfg, f) : 0;
+  b.valid = 1;
+  memcpy(blob_bytes, &b, sizeof b);
+  return 0;
+}
+
+int eulerb200_p2p_attach(eulerb200_ctx* c, const void* all_blobs)
+{
+  if (!c || !all_blobs) return -1;
+  if (!c->mailbox) return fail(c, -3, "eulerb200_p2p_export must be called first");
+  EB_CUDA(c, cudaSetDevice(c->device));
+  const P2PBlob* blobs = reinterpret_cast<const P2PBlob*>(all_blobs);
+  std::vector<char*> base(c->cfg.nranks, nullptr);
+  for (int f = 0; f < 6; f++) {
+    if (!c->remote[f]) continue;
+    const int r = c->cfg.nbr[f];
+    const P2PBlob& b = blobs[r];
+    if (!b.valid || b.rank != r) return fail(c, -3, "peer blob missing or out of order");
+    if (b.face_len[f ^ 1] != eb::face_len(c->cfg, f)) return fail(c, -3, "neighbour's ghost slab has a different size");
+    if (!base[r]) {
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, -3, std::string("cudaIpcOpenMemHandle failed (no peer access?): ") + cudaGetErrorString(e));
+      }
+      base[r] = (char*)p;
+      c->opened.push_back(p);
+    }
+    c->peer_base[f] = base[r];
+    // what I send through my face f lands in the neighbour's slab of the opposite face
+    for (int par = 0; par < 2; par++) c->peer_slab_off[f][par] = b.slab_off[par][f ^ 1];
+    c->peer_arrival_off[f] = b.arrival_off + (int64_t)sizeof(unsigned long long) * (f ^ 1);
+  }
+  c->p2p = true;
+  return 0;
+}
+
 int eulerb200_exchange_start(eulerb200_ctx* c, const double* const* w, void* stream)
 {
   if (!c || !w) return -1;
@@ -591,7 +731,7 @@ int eulerb200_ghost_face(eulerb200_ctx* c, const double* const* w, int32_t f, do
 {
   if (!c || !w || !dst || f < 0 || f >= 6) return -1;
   eb::GhostFace G;
-  eb::ghost_face(c->cfg, f, c->recv[f], &G);
+  eb::ghost_face(c->cfg, f, c->recv_cur[f], &G);
   const long nent = eb::face_len(c->cfg, f) / (5 + c->cfg.nchem);
   ghost_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, (cudaStream_t)stream>>>(face_geom(c, f, w), G, dst, nent);
   c->launches++;
@@ -656,6 +796,7 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
   // the halos, then evaluate the remaining shell as non-overlapping slabs.
   int rc = exchange_start(c, w, s);
   if (rc) return rc;
+  for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
   long lo[3], hi[3];
   bool interior = true;
   for (int d = 0; d < 3; d++) {
@@ -707,6 +848,7 @@ int eulerb200_rhs(eulerb200_ctx* c, double t, const double* const* w, double* co
   int32_t bits = 0;
   rc = eulerb200_state_flag(c, stream, &bits);
   if (rc) return rc;
+  if (bits & 8) return fail(c, -3, "halo exchange timed out waiting for a neighbour's ghost layers (peer-store transport)");
   if (bits) {
     char msg[160];
     snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port_no, n, nchem, bcs, outdir):
+def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -28,6 +28,7 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir):
     from __graft_entry__ import load_package
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
+    os.environ["EULERB200_HALO"] = transport
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     pkg = load_package()
@@ -36,12 +37,13 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir):
     u.xlbc, u.xrbc, u.ylbc, u.yrbc, u.zlbc, u.zrbc = bcs
     u.forcing = [0, 0, -0.1, 0, 0]
     assert u.SetupDecomp(myid=rank, nprocs=world, device=rank) == 0
+    assert u.halo_transport == transport
     w = oracle.random_state(n, nchem, seed=31)
     W3 = [w[f].reshape(n[2], n[1], n[0]) for f in range(5)] + ([w[5].reshape(n[2], n[1], n[0], nchem)] if nchem else [])
     sl = (slice(u.ks, u.ke + 1), slice(u.js, u.je + 1), slice(u.is_, u.ie + 1))
     wl = pkg.ManyVector([torch.from_numpy(np.ascontiguousarray(a[sl]).ravel()).cuda() for a in W3])
     wdot = pkg.ManyVector.new(u)
-    for _ in range(2):       # twice: buffers and events must be reusable
+    for _ in range(3):       # repeatedly: slabs (both parities), flags and events must be reusable
         assert pkg.fEuler(0.0, wl, wdot, u) == 0, u.last_error()
     u.cfl = 0.4
     ret, dt = pkg.stability(wl, 0.0, u)
@@ -53,21 +55,25 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,nchem,bcs", [
-    (2, (40, 24, 20), 2, [P, P, R, R, N, N]),
-    (2, (3, 40, 36), 0, [N] * 6),
-    (4, (24, 28, 20), 2, [P] * 6),
-    (8, (24, 24, 24), 10, [R] * 6),
-    (8, (3, 64, 48), 0, [N] * 6),
+@pytest.mark.parametrize("world,n,nchem,bcs,transport", [
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "p2p"),      # periodic in x over 2 ranks: both x-faces go to the same peer
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl"),
+    (2, (3, 40, 36), 0, [N] * 6, "p2p"),
+    (4, (24, 28, 20), 2, [P] * 6, "p2p"),
+    (4, (24, 28, 20), 2, [P] * 6, "nccl"),
+    (8, (24, 24, 24), 10, [R] * 6, "p2p"),
+    (8, (3, 64, 48), 0, [N] * 6, "nccl"),
 ])
-def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem, bcs):
+def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem, bcs, transport):
+    """transport: "p2p" = pack kernels store into the neighbour's ghost slab over NVLink (CUDA IPC)
+    and publish a sequence number; "nccl" = pack + grouped ncclSend/ncclRecv on a side stream."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
     import oracle
-    mp.spawn(_worker, args=(world, _free_port(), n, nchem, bcs, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, nchem, bcs, str(tmp_path), transport), nprocs=world, join=True)
     port = oracle.Port()
     w = oracle.random_state(n, nchem, seed=31)
     d = (1.0 / n[0], 1.0 / n[1], 1.0 / n[2])
