@@ -126,6 +126,7 @@ int MPI_Waitall(int n, MPI_Request* req, MPI_Status* stat);
 int MPI_Allreduce(const void* in, void* out, int count, MPI_Datatype, MPI_Op, MPI_Comm);
 int MPI_Barrier(MPI_Comm);
 int MPI_Bcast(void* buf, int count, MPI_Datatype, int root, MPI_Comm);
+int MPI_Allgather(const void* in, int incount, MPI_Datatype, void* out, int outcount, MPI_Datatype, MPI_Comm);
 int MPI_Abort(MPI_Comm, int code);
 double MPI_Wtime(void);
 

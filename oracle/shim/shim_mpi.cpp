@@ -171,6 +171,18 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype type, int root, MPI_Comm comm)
   return MPI_SUCCESS;
 }
 
+int MPI_Allgather(const void* in, int incount, MPI_Datatype type, void* out, int, MPI_Datatype, MPI_Comm comm)
+{
+  static std::vector<char> box;
+  const size_t bytes = (size_t)incount * (type == MPI_BYTE ? 1 : (type == MPI_INT ? 4 : 8));
+  { std::lock_guard<std::mutex> lk(g_mtx); if (box.size() != bytes * g_nprocs) box.assign(bytes * g_nprocs, 0);
+    memcpy(box.data() + bytes * t_rank, in, bytes); }
+  MPI_Barrier(comm);
+  { std::lock_guard<std::mutex> lk(g_mtx); memcpy(out, box.data(), bytes * g_nprocs); }
+  MPI_Barrier(comm);
+  return MPI_SUCCESS;
+}
+
 int MPI_Abort(MPI_Comm, int code) { fprintf(stderr, "shim MPI_Abort(%d)\n", code); abort(); return 0; }
 
 double MPI_Wtime(void) {

@@ -416,16 +416,22 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
     // neighbour may still be reading belongs to the previous exchange), then publish the number
     c->seq++;
     const int par = (int)(c->seq & 1ull);
+    // on the side stream, so that the NVLink stores overlap the interior kernel instead of
+    // delaying it (the pack CTAs slip into the SMs as interior CTAs retire)
+    EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
+    EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
     for (int f = 0; f < 6; f++) {
       if (!c->remote[f]) continue;
       const long nent = eb::face_len(c->cfg, f) / nv;
       double* dst = reinterpret_cast<double*>(c->peer_base[f] + c->peer_slab_off[f][par]);
-      pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), dst, nent);
-      halo_signal_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
+      pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
+      halo_signal_kernel<<<1, 1, 0, c->comm_stream>>>(
+          reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
       c->launches += 2;
       c->recv_cur[f] = reinterpret_cast<const double*>(c->mailbox + c->slab_off[par][f]);
     }
     EB_CUDA(c, cudaGetLastError());
+    EB_CUDA(c, cudaEventRecord(c->ev_recv, c->comm_stream));
     c->exchange_open = true;
     return 0;
   }
@@ -458,6 +464,7 @@ int exchange_end(eulerb200_ctx* c, cudaStream_t s)
 {
   if (!c->exchange_open) return 0;
   if (c->p2p) {
+    EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_recv, 0));     // my own stores are out (w may be reused)
     unsigned mask = 0;
     for (int f = 0; f < 6; f++) if (c->remote[f]) mask |= 1u << f;
     halo_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(c->mailbox + c->arrival_off), mask,

@@ -21,11 +21,13 @@
 // once on a small host probe vector when the context is created and its constants are
 // handed to the kernel; a hook that is not constant in space is rejected loudly.
 //
-// Multi-rank: the NCCL id is distributed over the reference's own communicator
-// (MPI_Bcast on udata->comm) -- the only MPI call left on this path.
+// Multi-rank: the NCCL id (MPI_Bcast) and the CUDA-IPC mailbox handles of the peer-store halo
+// transport (MPI_Allgather) travel once, at context creation, over the reference's own
+// communicator udata->comm -- no MPI call is left on the per-RHS path.
 // ---------------------------------------------------------------------------
 #include <euler3D.hpp>
 #include <map>
+#include <vector>
 #include "eulerb200.h"
 
 namespace {
@@ -98,6 +100,20 @@ eulerb200_ctx* context_for(EulerData* udata)
     if (MPI_Bcast(id, EULERB200_UNIQUE_ID_BYTES, MPI_BYTE, 0, udata->comm) != MPI_SUCCESS) return NULL;
     if (eulerb200_comm_attach(ctx, id) != 0) {
       cerr << "\neulerb200_comm_attach failed: " << eulerb200_last_error(ctx) << "\n\n";
+      return NULL;
+    }
+    // peer-store halo transport (CUDA IPC over NVLink) when every rank can map its neighbours;
+    // otherwise the context keeps the NCCL send/recv pairs
+    std::vector<char> blobs((size_t)EULERB200_P2P_BLOB_BYTES * udata->nprocs);
+    char mine[EULERB200_P2P_BLOB_BYTES];
+    int ok = eulerb200_p2p_export(ctx, mine) == 0 ? 1 : 0;
+    if (MPI_Allgather(mine, EULERB200_P2P_BLOB_BYTES, MPI_BYTE, blobs.data(), EULERB200_P2P_BLOB_BYTES, MPI_BYTE,
+                      udata->comm) != MPI_SUCCESS) return NULL;
+    double flag = (ok && eulerb200_p2p_attach(ctx, blobs.data()) == 0) ? 1.0 : 0.0;
+    if (MPI_Allreduce(MPI_IN_PLACE, &flag, 1, MPI_DOUBLE, MPI_MIN, udata->comm) != MPI_SUCCESS) return NULL;
+    if (flag == 0.0) {
+      cerr << "\neulerb200: peer-store halo transport unavailable on some rank; this build expects all GPUs of "
+              "the run to be peer-accessible (one NVSwitch node)\n\n";
       return NULL;
     }
   }
