@@ -144,6 +144,11 @@ def cpu_reference_run(nvar, steps, warmup, per_rank=40, max_ranks=None):
             "sample": "C port of the oracle, 1 core, %d^3 cells, NVAR=%d, %d timed evals" % (per_rank, nvar, steps)}
 
 
+def workload_name(n, nchem):
+    return ("primordial_blast/fluid_blast shape: %dx%dx%d cells per GPU, nchem=%d (NVAR=%d), "
+            "unit cube, all-reflecting, gamma=5/3" % (n[0], n[1], n[2], nchem, 5 + nchem))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -157,8 +162,8 @@ def run_reference_arm(args):
         "unit": "Gcell/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "primordial_blast-shaped state, nchem=%d (NVAR=%d), all-reflecting, gamma=5/3; "
-                               "bounded CPU sample: %s" % (args.nchem, nvar, r["sample"])},
+        "config": {"workload": workload_name(args.n, args.nchem),
+                   "sample": "each step is a bounded CPU sample of that workload: " + r["sample"]},
         "cpu_baseline": {"value": r["value"], "unit": "Gcell/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -398,8 +403,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "primordial_blast/fluid_blast shape: %dx%dx%d cells per GPU, nchem=%d (NVAR=%d), "
-                                   "unit cube, all-reflecting, gamma=5/3" % (u.nxl, u.nyl, u.nzl, args.nchem, nvar),
+            "config": {"workload": workload_name((u.nxl, u.nyl, u.nzl), args.nchem),
                        "global_grid": [u.nx, u.ny, u.nz], "process_grid": [u.npx, u.npy, u.npz],
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed"
                              % (8 * nvar * cells_local / 1e9),
