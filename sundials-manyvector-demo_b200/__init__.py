@@ -257,9 +257,10 @@ class EulerData:
         dist.broadcast(t, src=0, group=process_group)
         raw = bytes(t.cpu().numpy().tobytes())
         self._check(lib.eulerb200_comm_attach(self._ctx, C.create_string_buffer(raw, 128)), self._ctx)
-        # peer-store halo transport (CUDA IPC) unless EULERB200_HALO=nccl; every rank must agree
+        # halo transport: "nccl" (default: the one validated at 8 GPUs, profiles/README.md) or the
+        # peer-store transport over CUDA IPC with EULERB200_HALO=p2p; every rank must agree
         self.halo_transport = "nccl"
-        if os.environ.get("EULERB200_HALO", "p2p") != "nccl":
+        if os.environ.get("EULERB200_HALO", "nccl") == "p2p":
             blob = (C.c_char * 256)()
             ok = lib.eulerb200_p2p_export(self._ctx, blob) == 0
             mine = torch.frombuffer(bytearray(bytes(blob)), dtype=torch.uint8).clone()

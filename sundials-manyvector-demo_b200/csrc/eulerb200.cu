@@ -100,8 +100,7 @@ __device__ __forceinline__ long face_cell(const FaceGeom& g, long src, long a, l
 // index order, all NVAR values of a cell contiguous (euler3D.hpp:644-786).
 __global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
 {
-  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (e >= nent) return;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
   int d; long a, b, na;
   face_decode(g, e, d, a, b, na);
   const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
@@ -112,6 +111,7 @@ __global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, lon
 #pragma unroll
   for (int v = 0; v < 5; v++) o[v] = g.w[v][cell];
   for (int v = 0; v < g.nchem; v++) o[5 + v] = g.w[5][cell * g.nchem + v];
+  }
 }
 
 // Ghost layers of face f in the reference's receive-buffer layout, from the descriptor
