@@ -779,6 +779,7 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
                     int slow_mode, double energy_units)
 {
   if (!c || !w || !wdot) return -1;
+  EB_CUDA(c, cudaSetDevice(c->device));        // one context per GPU; the caller may have moved on
   for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++)
     if (!w[f] || !wdot[f]) return fail(c, -1, "NULL sub-vector pointer (utilities.cpp:31-58)");
   cudaStream_t s = (cudaStream_t)stream;
