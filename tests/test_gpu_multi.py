@@ -90,3 +90,58 @@ def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem
         for f, a in enumerate(R3):
             want = np.ascontiguousarray(a[sl]).ravel()
             assert np.abs(z["wdot%d" % f] - want).max() <= 1e-12 * np.abs(a).max()
+
+
+def _halo_worker(rank, world, port_no, nvar, outdir, transport):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    os.environ["EULERB200_HALO"] = transport
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    pkg = load_package()
+    n = (12, 12, 12)
+    u = pkg.EulerData(nchem=nvar - 5)
+    u.nx, u.ny, u.nz = n
+    assert u.SetupDecomp(myid=rank, nprocs=world, device=rank) == 0          # all-periodic by default
+    idx = np.arange(n[0] * n[1] * n[2])
+    i, j, k = idx % n[0], (idx // n[0]) % n[1], idx // (n[0] * n[1])
+    enc = lambda v: (0.001 * v + 1e-6 * i + 1e-9 * j + 1e-12 * k).reshape(n[2], n[1], n[0])
+    sl = (slice(u.ks, u.ke + 1), slice(u.js, u.je + 1), slice(u.is_, u.ie + 1))
+    subs = [torch.from_numpy(np.ascontiguousarray(enc(v)[sl]).ravel()).cuda() for v in range(5)]
+    if nvar > 5:
+        subs.append(torch.from_numpy(np.ascontiguousarray(np.stack([enc(v)[sl] for v in range(5, nvar)], axis=-1)).ravel()).cuda())
+    w = pkg.ManyVector(subs)
+    for rep in range(2):
+        assert u.ExchangeStart(w) == 0 and u.ExchangeEnd() == 0
+    torch.cuda.synchronize()
+    out = {"ext": np.array([u.is_, u.ie, u.js, u.je, u.ks, u.ke]), "nbr": np.array(u.nbrs)}
+    for f in range(6):
+        out["recv%d" % f] = u.recv_buffer(w, f).cpu().numpy()
+    np.savez(os.path.join(outdir, "halo%d.npz" % rank), **out)
+    dist.barrier()
+    u.FreeData()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nvar,transport", [(2, 5, "nccl"), (2, 7, "p2p"), (8, 7, "nccl"), (8, 5, "p2p")])
+def test_exchange_equals_the_references_own_receive_buffers(tmp_path, world, nvar, transport):
+    """communication_test_main.cpp on GPUs: after ExchangeStart/ExchangeEnd the six ghost slabs of
+    every rank must equal, entry for entry, what the REFERENCE's ExchangeStart/ExchangeEnd delivered
+    on the same 12^3 periodic grid with (field, i, j, k)-encoded values (tests/golden/exchange_*.npz,
+    produced by the unmodified reference on 2 and 8 virtual MPI ranks)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    mp.spawn(_halo_worker, args=(world, _free_port(), nvar, str(tmp_path), transport), nprocs=world, join=True)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "exchange_nvar%d.npz" % nvar))
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "halo%d.npz" % rank))
+        assert list(z["ext"]) == list(gold["p%d_r%d_ext" % (world, rank)])
+        assert [int(x) for x in z["nbr"]] == [int(x) for x in gold["p%d_r%d_nbr" % (world, rank)]]
+        for f in range(6):
+            assert np.array_equal(z["recv%d" % f], gold["p%d_r%d_recv%d" % (world, rank, f)]), (rank, f)
