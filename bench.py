@@ -46,7 +46,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -66,7 +66,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Call right before and right after the timed region: only samples in between count."""
+        import datetime
+        self.marks = getattr(self, "marks", []) + [datetime.datetime.now()]
+
     def stop(self):
+        import datetime
         res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return res
@@ -74,24 +80,31 @@ class ClockSampler:
             self.proc.terminate()
             self.proc.wait(timeout=5)
             self.out.close()
-            sm, smax, reasons = [], [], set()
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            rows = []
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); smax.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(p[1]), float(p[2]), p[5:9]))
                 except ValueError:
                     continue
-                for nm, v in zip(names, p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
-            if sm:
-                sm.sort()
-                res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                       "samples": len(sm)}
+            marks = getattr(self, "marks", [])
+            inside = [r for r in rows if len(marks) >= 2 and marks[0] <= r[0] <= marks[1]]
+            use = inside if inside else rows          # the sampler runs from before the warm-up steps
+            if use:
+                sm = sorted(r[1] for r in use)
+                reasons = set()
+                for r in use:
+                    for nm, v in zip(names, r[3]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+                res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in use),
+                       "reasons": sorted(reasons), "samples": len(use),
+                       "window": "timed region" if inside else "warm-up + timed region"}
         except Exception:
             pass
         return res
@@ -255,21 +268,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi takes a moment to start: begin before the warm-up
     for _ in range(args.warmup):
         ret = pkg.fEuler(0.0, w, wdot, u)
         assert ret == 0, u.last_error()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = u.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.mark()
     ev[0].record()
     for s in range(args.steps):
         ret = pkg.fEuler(0.0, w, wdot, u)
         ev[s + 1].record()
     barrier()
+    sampler.mark()
     clocks = sampler.stop() if rank == 0 else None
     assert ret == 0, u.last_error()
     launches = u.launch_count() - launches0
