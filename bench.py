@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ic", default="random", choices=["random", "primordial_blast"],
+                    help="synthetic state: seeded random admissible state (default, SURVEY.md 8(d)) or the "
+                         "reference's primordial_blast initial condition (needs --nchem 10)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -258,7 +261,12 @@ def main():
     cells_local = u.nxl * u.nyl * u.nzl
     cells_global = u.nx * u.ny * u.nz
 
-    w = pkg.ManyVector(synth_state(torch, u, 1234 + rank, gamma))
+    if args.ic == "primordial_blast":
+        pkg.problems.configure("primordial_blast", u)      # units only; BCs and gamma are already these
+        w = pkg.ManyVector.new(u)
+        assert pkg.problems.initial_conditions("primordial_blast", 0.0, w, u) == 0
+    else:
+        w = pkg.ManyVector(synth_state(torch, u, 1234 + rank, gamma))
     wdot = pkg.ManyVector.new(u)
     torch.cuda.synchronize()
 
@@ -416,7 +424,7 @@ def main():
             "metric": "fEuler cell-RHS evaluations per second", "value": value, "unit": "Gcell/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "data": "synthetic" if args.ic == "random" else "synthetic (primordial_blast initial condition)",
             "config": {"workload": workload_name((u.nxl, u.nyl, u.nzl), args.nchem),
                        "global_grid": [u.nx, u.ny, u.nz], "process_grid": [u.npx, u.npy, u.npz],
                        "l2": "inputs (%.1f GB per GPU) far larger than the 126 MB L2; no flush needed"

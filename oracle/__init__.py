@@ -36,7 +36,9 @@ def build_port(force=False):
     """Compile the C restatement (gcc only; works on the GPU box too)."""
     so = os.path.join(HERE, "liboracle.so")
     src = os.path.join(HERE, "euler_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    so_fma = os.path.join(HERE, "liboracle_fma.so")
+    if (force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+            or not os.path.exists(so_fma) or os.path.getmtime(so_fma) < os.path.getmtime(src)):
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     return so
 
@@ -91,10 +93,15 @@ def split_state(w, n, nchem):
 
 
 class Port:
-    """ctypes face of oracle/euler_oracle.c."""
+    """ctypes face of oracle/euler_oracle.c.  ``fma=True`` loads the FMA-contracted build, which
+    is not an oracle but a yardstick: |Port(fma=True) - Port()| is how far the reference's own
+    arithmetic moves under a different legal compilation of the same source."""
 
-    def __init__(self):
-        self.lib = C.CDLL(build_port())
+    def __init__(self, fma=False):
+        so = build_port()
+        if fma:
+            so = os.path.join(HERE, "liboracle_fma.so")
+        self.lib = C.CDLL(so)
         L = self.lib
         L.oracle_feuler.restype = C.c_int
         L.oracle_feuler.argtypes = [C.POINTER(_Cfg), _dp * 6, _dp * 6, _dp * 6, C.POINTER(C.c_int)]

@@ -6,6 +6,8 @@ executable, each providing ``initial_conditions``, ``external_forces`` and
     linear_advection_x | _y | _z              linear_advection.cpp
     rayleigh_taylor                           rayleigh_taylor.cpp
     hurricane_xy | hurricane_yz | hurricane_zx    hurricane.cpp
+    fluid_blast (nchem = 0) | primordial_blast (nchem = 10, fluid + tracer values only)
+                                              fluid_blast.cpp, primordial_blast.cpp:64-309
 
 plus the two diagnostics of io.cpp every driver prints: ``check_conservation`` (:504-541)
 and ``print_stats`` (:552-636).  States are built and reduced on the device (torch is the
@@ -24,6 +26,56 @@ def _coords(torch, u, device):
     z = (torch.arange(u.nzl, **f64) + (u.ks + 0.5)) * u.dz + u.zl
     Z, Y, X = torch.meshgrid(z, y, x, indexing="ij")       # flat index i + nxl*(j + nyl*k)
     return X.reshape(-1), Y.reshape(-1), Z.reshape(-1)
+
+
+class MT19937_64:
+    """std::mt19937_64 (the clump generator of fluid_blast.cpp:102) -- numpy only has the 32-bit
+    twister.  uniform(a, b) follows libstdc++'s uniform_real_distribution<double>:
+    a + (b - a) * double(x) / 2^64 with one 64-bit draw per value."""
+    N, M = 312, 156
+    MASK = (1 << 64) - 1
+
+    def __init__(self, seed):
+        self.mt = [0] * self.N
+        self.mt[0] = seed & self.MASK
+        for i in range(1, self.N):
+            self.mt[i] = (6364136223846793005 * (self.mt[i - 1] ^ (self.mt[i - 1] >> 62)) + i) & self.MASK
+        self.idx = self.N
+
+    def next(self):
+        if self.idx >= self.N:
+            mt, N, M = self.mt, self.N, self.M
+            for i in range(N):
+                x = (mt[i] & 0xFFFFFFFF80000000) | (mt[(i + 1) % N] & 0x7FFFFFFF)
+                xa = x >> 1
+                if x & 1:
+                    xa ^= 0xB5026F5AA96619E9
+                mt[i] = mt[(i + M) % N] ^ xa
+            self.idx = 0
+        y = self.mt[self.idx]
+        self.idx += 1
+        y ^= (y >> 29) & 0x5555555555555555
+        y ^= (y << 17) & 0x71D67FFFEDA60000
+        y ^= (y << 37) & 0xFFF7EEE000000000
+        y ^= y >> 43
+        return y & self.MASK
+
+    def uniform(self, a, b):
+        r = float(self.next()) / 18446744073709551616.0
+        if r >= 1.0:
+            r = 1.0 - 2.0 ** -53
+        return r * (b - a) + a
+
+
+def blast_clumps(u, max_strength):
+    """10*nprocs Gaussian clumps: centre, radius (cells) and strength (fluid_blast.cpp:98-128,
+    primordial_blast.cpp:102-123; MAX_CLUMP_STRENGTH is 10 resp. 5)."""
+    gen = MT19937_64(u.nprocs)
+    out = []
+    for _ in range(10 * u.nprocs):
+        cx, cy, cz = gen.uniform(u.xl, u.xr), gen.uniform(u.yl, u.yr), gen.uniform(u.zl, u.zr)
+        out.append((cx, cy, cz, gen.uniform(3.0, 6.0), gen.uniform(0.0, max_strength)))
+    return out
 
 
 def configure(problem, u):
@@ -47,8 +99,64 @@ def configure(problem, u):
         u.xr = u.yr = u.zr = 1.0
         u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = BC_NEUMANN
         u.gamma = 2.0
+    elif problem in ("fluid_blast", "primordial_blast"):
+        # tests/fluid_blast/input_fluid_blast.txt, tests/primordial_blast/input_primordial_blast_mr.txt
+        u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = BC_REFLECTING
+        u.gamma = 5.0 / 3.0
+        u.MassUnits, u.LengthUnits = 3.0e70, 3.0857e30
+        u.TimeUnits = 1.0e12 if problem == "fluid_blast" else 1.0e11
+        u.DensityUnits = u.MassUnits / u.LengthUnits / u.LengthUnits / u.LengthUnits      # euler3D.hpp:385-393
+        u.MomentumUnits = u.MassUnits / u.LengthUnits / u.LengthUnits / u.TimeUnits
+        u.EnergyUnits = u.MassUnits / u.LengthUnits / u.TimeUnits / u.TimeUnits
     else:
         raise ValueError("unknown problem %r" % problem)
+
+
+def _blast_state(problem, w, u, X, Y, Z):
+    """fluid_blast.cpp:140-264 / primordial_blast.cpp:180-297: clumpy neutral primordial gas at rest
+    plus a hot dense central clump; the ten tracers are the eight number densities, the electron
+    density and the gas energy."""
+    import torch
+    mH, kboltz, Hfrac = 1.67e-24, 1.3806488e-16, 0.76
+    m_amu = 1.66053904e-24
+    density0 = 1e2 * mH
+    # the two problem files differ in three constants (fluid_blast.cpp:50-58, primordial_blast.cpp:50-60)
+    fluid = problem == "fluid_blast"
+    max_strength, blast_density = (10.0, 10.0) if fluid else (5.0, 5.0)
+    blast_temp = 10.0 * 5.0 if fluid else 10.0 * (5.0 - 1.0)
+    density = torch.ones_like(X)
+    for cx, cy, cz, cr, cs in blast_clumps(u, max_strength):
+        cr = cr * u.dx
+        rsq = (X - cx).abs() ** 2 + (Y - cy).abs() ** 2 + (Z - cz).abs() ** 2
+        density = density + cs * torch.exp(-2.0 * rsq / cr / cr)
+    density = density * density0
+    cx, cy, cz = u.xl + 0.5 * (u.xr - u.xl), u.yl + 0.5 * (u.yr - u.yl), u.zl + 0.5 * (u.zr - u.zl)
+    cr = 0.1 * min(u.xr - u.xl, u.yr - u.yl, u.zr - u.zl)
+    rsq = (X - cx).abs() ** 2 + (Y - cy).abs() ** 2 + (Z - cz).abs() ** 2
+    bump = torch.exp(-2.0 * rsq / cr / cr)
+    density = density + density0 * blast_density * bump
+    T = 10.0 + blast_temp * bump
+    inside = rsq / cr / cr < 2.0
+    tiny, small = 1e-40, 1e-12
+    pick = lambda a: torch.where(inside, a * density, 1.0e-3 * density)
+    H2I, H2II, HII, HM, HeII, HeIII = pick(tiny), pick(tiny), pick(small), pick(tiny), pick(small), pick(small)
+    HeI = (1.0 - Hfrac) * density - HeII - HeIII
+    HI = density - (H2I + H2II + HII + HM + HeI + HeII + HeIII)
+    wH, wHe = 1.00794 * mH, 4.002602 * mH
+    nH2I, nH2II, nHII, nHM = H2I / (2 * wH), H2II / (2 * wH), HII / wH, HM / wH
+    nHeII, nHeIII, nHeI, nHI = HeII / wHe, HeIII / wHe, HeI / wHe, HI / wH
+    ndens = nH2I + nH2II + nHII + nHM + nHeII + nHeIII + nHeI + nHI
+    ge = (kboltz * T * ndens) / (density * (u.gamma - 1.0))
+    zero = torch.zeros_like(X)
+    for dst, src in zip(w.sub[:5], (density / u.DensityUnits, zero, zero, zero, ge / u.EnergyUnits)):
+        dst.copy_(src)
+    if u.nchem > 0:
+        if u.nchem != 10:
+            raise ValueError("primordial_blast carries 10 species")
+        de = (nHII + nHeII + 2 * nHeIII - nHM + nH2II) * mH
+        chem = torch.stack([nH2I, nH2II, nHI, nHII, nHM, nHeI, nHeII, nHeIII, de / m_amu, ge], dim=1)
+        w.sub[5].copy_(chem.reshape(-1))
+    return 0
 
 
 def initial_conditions(problem, t, w, u):
@@ -58,6 +166,8 @@ def initial_conditions(problem, t, w, u):
     X, Y, Z = _coords(torch, u, dev)
     zero = torch.zeros_like(X)
     mx, my, mz = zero.clone(), zero.clone(), zero.clone()
+    if problem in ("fluid_blast", "primordial_blast"):
+        return _blast_state(problem, w, u, X, Y, Z)
     if problem.startswith("sod"):                                   # sod.cpp:50-55,120-160
         s = {"x": X, "y": Y, "z": Z}[problem[-1]]
         left = s < 0.5

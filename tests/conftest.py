@@ -59,6 +59,22 @@ def rounding_floor(parts, gamma, d, ulps=32.0):
     return [ulps * EPS * float(x) * inv for x in S]
 
 
+@pytest.fixture(scope="session")
+def port_fma(oracle_mod):
+    return oracle_mod.Port(fma=True)
+
+
+def self_noise(port, port_fma, cfg, parts):
+    """Normwise distance between the oracle and the SAME source compiled with FMA contraction,
+    per sub-vector: the rounding-noise level of this particular state.  For O(1) states it is
+    ~2e-15; where the characteristic transform is ill-conditioned (c^2 << 1 in code units, as in
+    the primordial_blast set-up with c^2 ~ 1e-9) it reaches 5e-11, and no implementation other
+    than a bit-identical one can be closer to the reference than that."""
+    _, a, _ = port.feuler(cfg, parts)
+    _, b, _ = port_fma.feuler(cfg, parts)
+    return normwise_errors(b, a)
+
+
 def normwise_errors(got, ref, floor=None):
     """The parity metric (DESIGN.md "Tolerance"): per sub-vector
         max(0, max|got-ref| - floor_f) / scale_f ,   required <= 1e-12,

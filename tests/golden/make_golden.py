@@ -146,6 +146,21 @@ def main():
                 rec["%s_p%d" % (tag, nprocs)] = np.array([[-999]])     # SetupDecomp refused
         rec["%s_n" % tag] = np.array(n); rec["%s_bc" % tag] = np.array(bcs)
     np.savez_compressed(os.path.join(HERE, "decomp_tables.npz"), **rec)
+    # fluid_blast initial condition of the reference itself (fluid_blast.cpp:65-267): pins the
+    # mt19937_64 clump generator and the formulas restated in problems.py
+    import subprocess
+    import tempfile
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "fluid_blast"])
+    n = (14, 12, 10)
+    N = n[0] * n[1] * n[2]
+    with tempfile.TemporaryDirectory() as td:
+        out_path = os.path.join(td, "ic.bin")
+        subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "fluid_blast_ic")] + [str(x) for x in n] + [out_path],
+                              stdout=subprocess.DEVNULL)
+        flat = np.fromfile(out_path, dtype=np.float64)
+    arrs = [flat[f * N:(f + 1) * N].copy() for f in range(5)]
+    np.savez_compressed(os.path.join(HERE, "ic_fluid_blast.npz"), n=np.array(n), **{"w%d" % f: arrs[f] for f in range(5)})
+
     print("golden vectors written:", sorted(os.listdir(HERE)))
     print("max |wdot| per case:", out)
 

@@ -93,3 +93,27 @@ def test_fixed_step_and_cfl_hook(pkg, port):
     assert lim.evolve(0.1)[0] == 0
     dt_stab = ops.stability(NpVec(parts), 0.0)[1]
     assert lim.stats()["nst"] >= int(0.1 / dt_stab)      # the CFL bound, not the tolerance, set the steps
+
+
+def test_fluid_blast_initial_condition_matches_reference(pkg):
+    """problems.py's fluid_blast state (std::mt19937_64 clumps + central blast, restated from
+    fluid_blast.cpp:65-267) == the state the UNMODIFIED reference initial_conditions() produced
+    (tests/golden/ic_fluid_blast.npz, written by oracle/_ref/fluid_blast_ic)."""
+    import os
+    import torch
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ic_fluid_blast.npz"))
+    n = tuple(int(x) for x in z["n"])
+    u = pkg.EulerData()
+    u.nx, u.ny, u.nz = n
+    pkg.problems.configure("fluid_blast", u)
+    u.dx, u.dy, u.dz = 1.0 / n[0], 1.0 / n[1], 1.0 / n[2]          # what SetupDecomp would set on one rank
+    u.nxl, u.nyl, u.nzl = n
+    u.is_ = u.js = u.ks = 0
+    w = pkg.ManyVector([torch.zeros(n[0] * n[1] * n[2], dtype=torch.float64) for _ in range(5)])
+    assert pkg.problems.initial_conditions("fluid_blast", 0.0, w, u) == 0
+    for f in range(5):
+        ref = z["w%d" % f]
+        assert np.abs(w.sub[f].numpy() - ref).max() <= 4e-16 * max(np.abs(ref).max(), 1e-300)
+    # the generator itself: first draws of std::mt19937_64(5489) are 14514284786278117030, 4620546740167642908
+    g = pkg.problems.MT19937_64(5489)
+    assert g.next() == 14514284786278117030 and g.next() == 4620546740167642908

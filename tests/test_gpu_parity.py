@@ -6,7 +6,7 @@ max|gpu - ref| / max|ref| <= 1e-12 in FP64.
 import numpy as np
 import pytest
 
-from conftest import normwise_errors, rounding_floor
+from conftest import normwise_errors, rounding_floor, self_noise
 from helpers import gpu_feuler, make_udata, oracle_feuler
 
 pytestmark = pytest.mark.gpu
@@ -65,3 +65,40 @@ def test_illegal_state_returns_minus_one(pkg, oracle_mod, port):
         assert ret == -1 and ret_ref == -1
         assert "flag = %d" % mask in u.last_error()
         u.FreeData()
+
+
+@pytest.mark.parametrize("problem,nchem", [("fluid_blast", 0), ("primordial_blast", 10)])
+def test_blast_states_match_oracle(pkg, port, port_fma, problem, nchem):
+    """The BASELINE.json fluid_blast / primordial_blast configuration at a size the oracle can do:
+    clumpy density + central blast, tracers spanning 1e-38 ... 1e2 (number densities of a nearly
+    neutral primordial gas), all-reflecting, gamma 5/3 -- the epsilon-dominated WENO regime."""
+    import torch
+    n = (24, 20, 18)
+    u = pkg.EulerData(nchem=nchem)
+    u.nx, u.ny, u.nz = n
+    pkg.problems.configure(problem, u)
+    assert u.SetupDecomp(device=0) == 0
+    w = pkg.ManyVector.new(u)
+    assert pkg.problems.initial_conditions(problem, 0.0, w, u) == 0
+    parts = [s.cpu().numpy() for s in w.sub] + ([None] if nchem == 0 else [])
+    wdot = pkg.ManyVector.new(u)
+    assert pkg.fEuler(0.0, w, wdot, u) == 0, u.last_error()
+    ret, ref, _ = oracle_feuler(port, u, parts)
+    assert ret == 0
+    got = [s.cpu().numpy() for s in wdot.sub] + ([None] if nchem == 0 else [])
+    # c^2 ~ 1e-7 ... 1e-9 in code units here: the eigenvector matrices carry 1/c^2 (utilities.cpp:
+    # 309-364) and the reference itself moves by up to 5e-11 when recompiled with FMA contraction.
+    # Bar: 1e-12, or 8x that self-noise where it is larger.
+    cfg = port.cfg(n, nchem, (u.dx, u.dy, u.dz), u.gamma, u.bcs, forcing=u.forcing)
+    noise = self_noise(port, port_fma, cfg, parts)
+    errs = normwise_errors(got, ref, rounding_floor(parts, u.gamma, (u.dx, u.dy, u.dz)))
+    for e, nz in zip(errs, noise):
+        assert e <= max(TOL, 8.0 * nz), (errs, noise)
+    if nchem:                       # per species too: each tracer against its own scale
+        g5, r5 = got[5].reshape(-1, nchem), ref[5].reshape(-1, nchem)
+        c5 = parts[5].reshape(-1, nchem)
+        for v in range(nchem):
+            scale = max(np.abs(r5[:, v]).max(), 1e-300)
+            lam = 2.0 * (1.0 / u.dx + 1.0 / u.dy + 1.0 / u.dz) * 1e-4          # (|u|+c) ~ 1e-4 here
+            assert np.abs(g5[:, v] - r5[:, v]).max() <= TOL * scale + 64 * 2.2e-16 * np.abs(c5[:, v]).max() * lam, v
+    u.FreeData()
