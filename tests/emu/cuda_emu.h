@@ -64,6 +64,7 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
   gdim() = grid; bdim() = block;
   const int T = block.x * block.y * block.z;
   std::vector<char> smem(shmem + 64);
+  std::vector<std::vector<char> > stacks(T, std::vector<char>(96 * 1024));   // reused by every CTA
   for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -73,12 +74,11 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
         fibers().assign(T, Fiber());
         for (int t = 0; t < T; t++) {
           Fiber& f = fibers()[t];
-          f.stack.resize(256 * 1024);
           f.done = false;
           f.tid.x = t % block.x; f.tid.y = (t / block.x) % block.y; f.tid.z = t / (block.x * block.y);
           getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = f.stack.data();
-          f.ctx.uc_stack.ss_size = f.stack.size();
+          f.ctx.uc_stack.ss_sp = stacks[t].data();
+          f.ctx.uc_stack.ss_size = stacks[t].size();
           f.ctx.uc_link = &sched_ctx();
           makecontext(&f.ctx, (void (*)())L::entry, 0);
         }

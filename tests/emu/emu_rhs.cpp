@@ -8,7 +8,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux)
+                       int threads, int use_aux, double energy_units)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -22,6 +22,15 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
   for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
   P.slow_mode = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
+  if (energy_units > 0.0) {        // fslow mode: the energy rebuild that aux_kernel does on the device
+    P.slow_mode = 1;
+    P.inv_energy_units = 1.0 / energy_units;
+    P.et_rw = const_cast<double*>(w[4]);
+    const long N = P.nx * P.ny * P.nz;
+    for (long c = 0; c < N; c++)
+      P.et_rw[c] = w[5][c * P.nchem + (P.nchem - 1)] * P.inv_energy_units
+                   + 0.5 / w[0][c] * (w[1][c] * w[1][c] + w[2][c] * w[2][c] + w[3][c] * w[3][c]);
+  }
   if (use_aux) {
     const long N = P.nx * P.ny * P.nz;
     for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);

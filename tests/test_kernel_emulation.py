@@ -97,3 +97,27 @@ def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle
         want = [np.ascontiguousarray(a[b["sl"]]).ravel() for a in R3]
         assert not any(np.isnan(o).any() for o in out)
         assert max(normwise_errors(out, want)) <= 1e-12
+
+
+def test_emulated_slow_mode_matches_reference_sequence(emu, oracle_mod, port):
+    """fslow on the CPU tier: energy rebuild, fEuler, etdot moved into the last
+    species -- the kernel's redirected stores against the reference's sequence around the oracle."""
+    n, nchem, eu = (34, 9, 8), 4, 2.5e3
+    bcs = [R] * 6
+    d = (0.1, 0.2, 0.3)
+    w = oracle_mod.random_state(n, nchem, seed=12)
+    chem = w[5].reshape(-1, nchem)
+    chem[:, -1] = eu * (2.0 + chem[:, -1])
+    w[4][:] = -7.0                                     # must be rebuilt, not read
+    ref_w = [x.copy() for x in w]
+    ref_w[4] = chem[:, -1] * (1.0 / eu) + 0.5 / w[0] * (w[1] ** 2 + w[2] ** 2 + w[3] ** 2)
+    ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, energy_units=eu)
+    assert ret == 0 and bits == 0
+    assert np.array_equal(w[4], ref_w[4])
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), ref_w)
+    ref[5].reshape(-1, nchem)[:, -1] = ref[4]
+    ref[4] = np.zeros_like(ref[4])
+    assert np.all(got[4] == 0.0)
+    floor = rounding_floor(ref_w, 1.4, d)
+    floor[4] = 0.0
+    assert max(normwise_errors(got, ref, floor)) <= 1e-12
