@@ -289,6 +289,8 @@ struct eulerb200_ctx {
   ncclComm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
+  cudaStream_t slab_stream[2] = {nullptr, nullptr};      // boundary slabs run side by side
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool exchange_open = false;
 
   // staging for eulerb200_rhs_host (allocated on first use)
@@ -587,6 +589,11 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     EB_CREATE(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
     EB_CREATE(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     EB_CREATE(cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
+    EB_CREATE(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int h = 0; h < 2; h++) {
+      EB_CREATE(cudaStreamCreateWithFlags(&c->slab_stream[h], cudaStreamNonBlocking));
+      EB_CREATE(cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming));
+    }
   }
 #undef EB_CREATE
   *out = c;
@@ -614,6 +621,11 @@ int eulerb200_destroy(eulerb200_ctx* c)
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
   if (c->ev_recv) cudaEventDestroy(c->ev_recv);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int h = 0; h < 2; h++) {
+    if (c->slab_stream[h]) cudaStreamDestroy(c->slab_stream[h]);
+    if (c->ev_join[h]) cudaEventDestroy(c->ev_join[h]);
+  }
   for (int q = 0; q < 4; q++) if (c->aux[q]) cudaFree(c->aux[q]);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -829,12 +841,24 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     const long d0[3] = {0, hi[1], lo[2]}, d1[3] = {n[0], n[1], hi[2]};            // y-high
     const long e0[3] = {0, lo[1], lo[2]}, e1[3] = {lo[0], hi[1], hi[2]};          // x-low
     const long f0[3] = {hi[0], lo[1], lo[2]}, f1[3] = {n[0], hi[1], hi[2]};       // x-high
-    if ((rc = launch_box(c, P, a0, a1, s))) return rc;
-    if ((rc = launch_box(c, P, b0, b1, s))) return rc;
-    if ((rc = launch_box(c, P, c0, c1, s))) return rc;
-    if ((rc = launch_box(c, P, d0, d1, s))) return rc;
-    if ((rc = launch_box(c, P, e0, e1, s))) return rc;
-    if ((rc = launch_box(c, P, f0, f1, s))) return rc;
+    // the slabs are independent and individually too small to fill the GPU: spread them over the
+    // compute stream and two helper streams, then join
+    const long* box[6][2] = {{a0, a1}, {b0, b1}, {c0, c1}, {d0, d1}, {e0, e1}, {f0, f1}};
+    cudaStream_t lane[3] = {s, c->slab_stream[0], c->slab_stream[1]};
+    EB_CUDA(c, cudaEventRecord(c->ev_fork, s));
+    for (int h = 0; h < 2; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_fork, 0));
+    int q = 0;
+    for (int b = 0; b < 6; b++) {
+      bool empty = false;
+      for (int d = 0; d < 3; d++) if (box[b][1][d] <= box[b][0][d]) empty = true;
+      if (empty) continue;
+      if ((rc = launch_box(c, P, box[b][0], box[b][1], lane[q % 3]))) return rc;
+      q++;
+    }
+    for (int h = 0; h < 2; h++) {
+      EB_CUDA(c, cudaEventRecord(c->ev_join[h], c->slab_stream[h]));
+      EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[h], 0));
+    }
   }
   return 0;
 }
