@@ -187,7 +187,7 @@ class ERKStep:
             self.h = self._initial_step(tout)
         steps_here = 0
         while self.t < tout * (1 - 1e-14) - 1e-300:
-            if steps_here >= self.o.mxsteps:
+            if steps_here >= (self.o.mxsteps if self.o.mxsteps > 0 else 500):     # 0 => ARKODE's default
                 return -1, self.t
             h = self.h
             if self.o.hmax > 0 and not self.o.fixedstep:

@@ -8,8 +8,11 @@
 //
 //   euler3d_b200 --problem=sod_x -f input_sod.txt [--nx=400 --rtol=1e-6 ...]
 //
-// Problems (chosen at link time in the reference, by name here): sod_{x,y,z},
-// linear_advection_{x,y,z}, rayleigh_taylor, hurricane_{xy,yz,zx}.
+// Problems (chosen at link time in the reference, by name here; host/problems.hpp): sod_{x,y,z},
+// linear_advection_{x,y,z}, rayleigh_taylor, hurricane_{xy,yz,zx}, fluid_blast, primordial_blast
+// (fluid + passive tracers).  --nchem=<int> plays the part of the reference's compile-time NVAR
+// (nchem = NVAR - 5, euler3D.hpp:52-59).  --output=1 writes output-<iout>.eb200 files (the flat
+// stand-in for output_solution's HDF5 files), --restart=<iout> starts from one (io.cpp:940).
 // The state lives on the GPU for the whole run; this file contains no CUDA: device memory,
 // the right-hand side, the stage combinations and the error norm all go through the C ABI
 // of include/eulerb200.h.  The time integrator is the embedded explicit Runge-Kutta loop
@@ -26,10 +29,11 @@
 #include <string>
 #include <vector>
 #include "eulerb200.h"
+#include "problems.hpp"
 
 namespace {
 
-const double PI = 3.14159265358979323846;
+using eb_problems::Problem;
 
 struct Inputs {
   std::map<std::string, double> v;
@@ -74,93 +78,6 @@ Vec new_vec(long N, int nchem)
   return v;
 }
 void free_vec(Vec& v) { for (int f = 0; f < v.nsub; f++) eulerb200_device_free(v.sub[f]); }
-
-struct Problem {
-  std::string name;
-  long nx, ny, nz;
-  double xl, xr, yl, yr, zl, zr, gamma;
-  double dx() const { return (xr - xl) / nx; }
-  double dy() const { return (yr - yl) / ny; }
-  double dz() const { return (zr - zl) / nz; }
-  char axis() const { return name[name.size() - 1]; }
-};
-
-// exact Riemann solution of the Sod tube (sod.cpp:214-379; pL > pR branch)
-double fsecant(double p4, double p1, double p5, double rho1, double rho5, double g)
-{
-  const double z = p4 / p5 - 1.0, c1 = sqrt(g * p1 / rho1), c5 = sqrt(g * p5 / rho5);
-  const double fact = (g - 1.0) / (2 * g) * (c5 / c1) * z / sqrt(1.0 + (g + 1.0) / (2 * g) * z);
-  return p1 * pow(1.0 - fact, 2 * g / (g - 1.0)) - p4;
-}
-void exact_riemann(double t, double x, double xI, double g, double& rho, double& u, double& p)
-{
-  const double rho1 = 1.0, p1 = 1.0, rho5 = 0.125, p5 = 0.1;
-  double p40 = p1, p41 = p5, f0 = fsecant(p40, p1, p5, rho1, rho5, g), p4 = p41;
-  for (int it = 0; it < 50; it++) {
-    const double f1 = fsecant(p41, p1, p5, rho1, rho5, g);
-    if (f1 == f0) break;
-    p4 = p41 - (p41 - p40) * f1 / (f1 - f0);
-    if (fabs(p4 - p41) / fabs(p41) < 1e-14) break;
-    p40 = p41; p41 = p4; f0 = f1;
-  }
-  const double z = p4 / p5 - 1.0, c5 = sqrt(g * p5 / rho5), gm1 = g - 1.0, gp1 = g + 1.0;
-  const double fact = sqrt(1.0 + 0.5 * gp1 * z / g);
-  const double u4 = c5 * z / (g * fact), rho4 = rho5 * (1.0 + 0.5 * gp1 * z / g) / (1.0 + 0.5 * gm1 * z / g);
-  const double w = c5 * fact, p3 = p4, u3 = u4, rho3 = rho1 * pow(p3 / p1, 1.0 / g);
-  const double c1 = sqrt(g * p1 / rho1), c3 = sqrt(g * p3 / rho3);
-  const double xsh = xI + w * t, xcd = xI + u3 * t, xft = xI + (u3 - c3) * t, xhd = xI - c1 * t;
-  if (x < xhd) { rho = rho1; p = p1; u = 0.0; }
-  else if (x < xft) {
-    u = 2.0 / gp1 * (c1 + (x - xI) / t);
-    const double f = 1.0 - 0.5 * gm1 * u / c1;
-    rho = rho1 * pow(f, 2.0 / gm1); p = p1 * pow(f, 2.0 * g / gm1);
-  }
-  else if (x < xcd) { rho = rho3; p = p3; u = u3; }
-  else if (x < xsh) { rho = rho4; p = p4; u = u4; }
-  else { rho = rho5; p = p5; u = 0.0; }
-}
-
-// Analytic / initial state of cell (i,j,k) at time t; returns false if the problem has no
-// analytic solution for t > 0 (then only t = t0 is meaningful).
-bool state_at(const Problem& P, double t, long i, long j, long k, double w[5])
-{
-  const double x = (i + 0.5) * P.dx() + P.xl, y = (j + 0.5) * P.dy() + P.yl, z = (k + 0.5) * P.dz() + P.zl;
-  double rho = 1.0, m[3] = {0, 0, 0}, p = 1.0;
-  bool analytic = true;
-  if (P.name.compare(0, 3, "sod") == 0) {
-    const int a = P.axis() - 'x';
-    const double s = a == 0 ? x : (a == 1 ? y : z);
-    double u = 0.0;
-    if (t > 0.0) exact_riemann(t, s, 0.5, P.gamma, rho, u, p);
-    else { rho = s < 0.5 ? 1.0 : 0.125; p = s < 0.5 ? 1.0 : 0.1; }
-    m[a] = rho * u;
-  } else if (P.name.compare(0, 16, "linear_advection") == 0) {
-    const int a = P.axis() - 'x';
-    const double s = a == 0 ? x : (a == 1 ? y : z);
-    rho = 1.0 + 0.1 * sin(2.0 * PI * (s - 0.5 * t));
-    m[a] = 0.5 * rho;
-  } else if (P.name == "rayleigh_taylor") {
-    rho = y > 0.0 ? 2.0 : 1.0;
-    m[1] = rho * 0.01 * (1.0 + cos(4.0 * PI * x)) * (1.0 + cos(3.0 * PI * y));
-    p = 2.5 - 0.1 * rho * y;
-    analytic = false;
-  } else if (P.name.compare(0, 9, "hurricane") == 0) {
-    const std::string pl = P.name.substr(P.name.size() - 2);
-    const double a = pl == "xy" ? x : (pl == "zx" ? z : y), b = pl == "xy" ? y : (pl == "zx" ? x : z);
-    double r = sqrt(a * a + b * b);
-    if (r == 0.0) r = 1e-14;
-    const double ma = 10.0 * (b / r), mb = -10.0 * (a / r);
-    if (pl == "xy") { m[0] = ma; m[1] = mb; } else if (pl == "zx") { m[2] = ma; m[0] = mb; } else { m[1] = ma; m[2] = mb; }
-    p = 25.0;
-    analytic = false;
-  } else {
-    fprintf(stderr, "unknown problem '%s'\n", P.name.c_str());
-    exit(1);
-  }
-  w[0] = rho; w[1] = m[0]; w[2] = m[1]; w[3] = m[2];
-  w[4] = p / (P.gamma - 1.0) + (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) * 0.5 / rho;      // eos_inv
-  return analytic;
-}
 
 // embedded explicit Runge-Kutta tables: ARKODE's defaults for order 2, 3, 4
 struct Table { int s, p, q; double A[5][5], b[5], bh[5]; };
@@ -315,13 +232,18 @@ int main(int argc, char** argv)
   P.xl = in.get("xl", 0); P.xr = in.get("xr", 1); P.yl = in.get("yl", 0); P.yr = in.get("yr", 1);
   P.zl = in.get("zl", 0); P.zr = in.get("zr", 1);
   P.gamma = in.get("gamma", 1.4);
-  const double t0 = in.get("t0", 0.0), tf = in.get("tf", 1.0);
+  P.nchem = (int)in.get("nchem", 0);
+  P.MassUnits = in.get("MassUnits", 1.0); P.LengthUnits = in.get("LengthUnits", 1.0); P.TimeUnits = in.get("TimeUnits", 1.0);
+  double t0 = in.get("t0", 0.0);
+  const double tf = in.get("tf", 1.0);
   const int nout = (int)in.get("nout", 10), showstats = (int)in.get("showstats", 0);
+  const int write_files = (int)in.get("output", 0), restart = (int)in.get("restart", -1);
+  if (P.nchem < 0 || P.nchem > 64) { fprintf(stderr, "illegal nchem = %d\n", P.nchem); return 1; }
 
   eulerb200_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.nxl = P.nx; cfg.nyl = P.ny; cfg.nzl = P.nz;
-  cfg.nchem = 0; cfg.device = -1;
+  cfg.nchem = P.nchem; cfg.device = -1;
   cfg.dx = P.dx(); cfg.dy = P.dy(); cfg.dz = P.dz();
   cfg.gamma = P.gamma;
   const char* bcn[6] = {"xlbc", "xrbc", "ylbc", "yrbc", "zlbc", "zrbc"};
@@ -343,49 +265,61 @@ int main(int argc, char** argv)
   printf("   bdry cond (0=per, 1=Neu, 2=Dir, 3=refl): [%d, %d] x [%d, %d] x [%d, %d]\n",
          cfg.bc[0], cfg.bc[1], cfg.bc[2], cfg.bc[3], cfg.bc[4], cfg.bc[5]);
   printf("   gamma: %g\n   spatial grid: %ld x %ld x %ld\n", P.gamma, P.nx, P.ny, P.nz);
+  if (P.nchem > 0) printf("   num chemical species: %d\n", P.nchem);
 
   const long N = P.nx * P.ny * P.nz;
   Stepper S;
   S.ctx = ctx;
   S.T = make_table((int)in.get("order", 4));
-  S.nglobal = 5 * N;
+  S.nglobal = (5 + P.nchem) * N;
   S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
   S.fixedstep = (int)in.get("fixedstep", 0);
   S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
   S.cfl = in.get("cfl", 0);
   S.mxsteps = (int)in.get("mxsteps", 5000);
+  if (S.mxsteps <= 0) S.mxsteps = 500;                        // 0 => ARKODE's default (MXSTEP_DEFAULT)
   auto dflt = [&](const char* k, double d) { const double x = in.get(k, 0); return x != 0 ? x : d; };
   S.safety = dflt("safety", 0.96); S.bias = dflt("bias", 1.5); S.growth = dflt("growth", 20.0);
   S.k1 = dflt("k1", 0.58); S.k2 = dflt("k2", 0.21); S.k3 = dflt("k3", 0.1);
   S.etamx1 = dflt("etamx1", 1e4); S.etamxf = dflt("etamxf", 0.3);
   S.maxnef = (int)dflt("maxnef", 7);
   S.t = t0;
-  S.w = new_vec(N, 0); S.ytmp = new_vec(N, 0); S.yerr = new_vec(N, 0);
-  for (int i = 0; i < S.T.s; i++) S.k[i] = new_vec(N, 0);
+  S.w = new_vec(N, P.nchem); S.ytmp = new_vec(N, P.nchem); S.yerr = new_vec(N, P.nchem);
+  for (int i = 0; i < S.T.s; i++) S.k[i] = new_vec(N, P.nchem);
 
-  // initial conditions (host, then one copy to the device)
+  // initial conditions or restart file (host, then one copy to the device)
   std::vector<std::vector<double>> host(5, std::vector<double>(N));
+  std::vector<double> host_chem((size_t)N * P.nchem);
+  double* const hf[5] = {host[0].data(), host[1].data(), host[2].data(), host[3].data(), host[4].data()};
   bool analytic = true;
-  for (long k = 0; k < P.nz; k++)
-    for (long j = 0; j < P.ny; j++)
-      for (long i = 0; i < P.nx; i++) {
-        double w5[5];
-        analytic = state_at(P, t0, i, j, k, w5);
-        const long c = i + P.nx * (j + P.ny * k);
-        for (int f = 0; f < 5; f++) host[f][c] = w5[f];
-      }
+  if (eb_problems::initial_conditions(P, t0, hf, host_chem.data(), &analytic) != 0) return 1;
+  if (restart >= 0) {
+    if (eb_problems::read_solution(eb_problems::solution_name(restart), P, &t0, hf, host_chem.data()) != 0) return 1;
+    printf("   restarting from %s at t = %g\n", eb_problems::solution_name(restart).c_str(), t0);
+    S.t = t0;
+  }
   for (int f = 0; f < 5; f++) eulerb200_copy_to_device(S.w.sub[f], host[f].data(), sizeof(double) * N);
+  if (P.nchem > 0) eulerb200_copy_to_device(S.w.sub[5], host_chem.data(), sizeof(double) * N * P.nchem);
 
   double mass0 = -1, energy0 = -1;
+  int iout_file = restart >= 0 ? restart : 0;
   auto outputs = [&](double t, int firstlast) {
     for (int f = 0; f < 5; f++) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N);
+    if (write_files) {                                        // output_solution, io.cpp:716-930
+      if (P.nchem > 0) eulerb200_copy_to_host(host_chem.data(), S.w.sub[5], sizeof(double) * N * P.nchem);
+      if (eb_problems::write_solution(eb_problems::solution_name(iout_file), P, t, hf, host_chem.data()) != 0) {
+        fprintf(stderr, "output_solution: cannot write %s\n", eb_problems::solution_name(iout_file).c_str());
+        exit(1);
+      }
+      iout_file++;
+    }
     if (analytic) {                                           // output_diagnostics of the problem file
       double errI[5] = {0, 0, 0, 0, 0}, errR[5] = {0, 0, 0, 0, 0};
       for (long k = 0; k < P.nz; k++)
         for (long j = 0; j < P.ny; j++)
           for (long i = 0; i < P.nx; i++) {
             double w5[5];
-            state_at(P, t, i, j, k, w5);
+            eb_problems::state_at(P, t, i, j, k, w5);
             const long c = i + P.nx * (j + P.ny * k);
             for (int f = 0; f < 5; f++) {
               const double e = fabs(w5[f] - host[f][c]);
@@ -396,11 +330,28 @@ int main(int argc, char** argv)
       printf("     errR = %9.2e  %9.2e  %9.2e  %9.2e  %9.2e\n", sqrt(errR[0] / N), sqrt(errR[1] / N),
              sqrt(errR[2] / N), sqrt(errR[3] / N), sqrt(errR[4] / N));
     }
-    if (showstats) {                                          // print_stats, io.cpp:552-636
-      double rms[5];
-      for (int f = 0; f < 5; f++) { double s = 0; for (long c = 0; c < N; c++) s += host[f][c] * host[f][c]; rms[f] = sqrt(s / N); }
-      if (firstlast == 0) printf("\n      t       ||rho||   ||mx||    ||my||    ||mz||    ||et||      nst\n");
-      printf("  %9.1e %9.1e %9.1e %9.1e %9.1e %9.1e  %6ld\n", t, rms[0], rms[1], rms[2], rms[3], rms[4], S.nst);
+    if (showstats) {                                          // print_stats (CGS values), io.cpp:552-636
+      const double su[5] = {P.DensityUnits(), P.MomentumUnits(), P.MomentumUnits(), P.MomentumUnits(), P.EnergyUnits()};
+      if (firstlast == 0) {
+        printf("\n      t       ||rho||   ||mx||    ||my||    ||mz||    ||et||   ");
+        for (int v = 0; v < P.nchem; v++) printf(" ||c%d||   ", v);
+        printf("   nst\n");
+      }
+      printf("  %9.1e", t);
+      for (int f = 0; f < 5; f++) {
+        double s = 0;
+        for (long c = 0; c < N; c++) s += (host[f][c] * su[f]) * (host[f][c] * su[f]);
+        printf(" %9.1e", sqrt(s / N));
+      }
+      if (P.nchem > 0) {
+        if (!write_files) eulerb200_copy_to_host(host_chem.data(), S.w.sub[5], sizeof(double) * N * P.nchem);
+        for (int v = 0; v < P.nchem; v++) {
+          double s = 0;
+          for (long c = 0; c < N; c++) s += host_chem[c * P.nchem + v] * host_chem[c * P.nchem + v];
+          printf(" %9.1e", sqrt(s / N));
+        }
+      }
+      printf("  %6ld\n", S.nst);
     }
   };
   auto conservation = [&]() {                                 // check_conservation, io.cpp:504-541

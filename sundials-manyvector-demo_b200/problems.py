@@ -10,7 +10,9 @@ executable, each providing ``initial_conditions``, ``external_forces`` and
                                               fluid_blast.cpp, primordial_blast.cpp:64-309
 
 plus the two diagnostics of io.cpp every driver prints: ``check_conservation`` (:504-541)
-and ``print_stats`` (:552-636).  States are built and reduced on the device (torch is the
+and ``print_stats`` (:552-636), and ``output_solution`` / ``read_restart`` (:716-1150) on a flat
+file with the reference's dataset order (no HDF5 in this image; the same ``.eb200`` files are
+written and read by the native driver, host/problems.hpp).  States are built and reduced on the device (torch is the
 array plumbing here; none of this is on the timed path).  The exact Riemann solution used
 by the Sod diagnostics (sod.cpp:214-379) is evaluated on the host per x-location.
 """
@@ -352,3 +354,110 @@ def print_stats(t, w, u, nst, group=None, quiet=False):
     if u.myid == 0 and not quiet:
         print("  %9.1e " % t + " ".join("%9.1e" % r for r in rms) + "  %6d" % nst)
     return rms
+
+
+# ---- solution files (output_solution / read_restart, io.cpp:716-1150) ---------------------
+# output-<iout>.eb200, little-endian:  char[8] "EB200OUT" | int32 version = 1 | int32 nchem |
+# int64 nx, ny, nz | double time | double domain[6] = zl, zr, yl, yr, xl, xr (io.cpp:827-829) |
+# 5 + nchem datasets of nx*ny*nz doubles, x fastest, in the reference's order and under the
+# reference's names; the fluid fields are stored in CGS (scaled by the unit factors, io.cpp:887-891).
+SOLUTION_MAGIC = b"EB200OUT"
+SOLUTION_HEADER_BYTES = 8 + 4 + 4 + 3 * 8 + 8 + 6 * 8
+FLUID_DATASETS = ("Density", "x-Momentum", "y-Momentum", "z-Momentum", "TotalEnergy")
+
+
+def solution_name(iout):
+    return "output-%07i.eb200" % iout
+
+
+def dataset_names(nchem):
+    return list(FLUID_DATASETS) + ["Chemical-%03d" % v for v in range(nchem)]
+
+
+def _unit_scales(u):
+    d, m, e = (float(getattr(u, k, 1.0)) for k in ("DensityUnits", "MomentumUnits", "EnergyUnits"))
+    return [d, m, m, m, e]
+
+
+def _barrier(u, group):
+    if u.nprocs > 1:
+        import torch.distributed as dist
+        dist.barrier(group=group)
+
+
+def output_solution(t, w, u, iout, directory=".", group=None):
+    """``output_solution``: every rank stores its sub-box of every field into the one shared file
+    (the reference does the same through an MPI-IO hyperslab, io.cpp:872-884).  Returns 0 / -1."""
+    import os
+    import struct
+    import numpy as np
+    path = os.path.join(directory, solution_name(iout))
+    N = u.nx * u.ny * u.nz
+    nds = 5 + u.nchem
+    try:
+        if u.myid == 0:
+            with open(path, "wb") as fp:
+                fp.write(SOLUTION_MAGIC + struct.pack("<iiqqqd6d", 1, u.nchem, u.nx, u.ny, u.nz, float(t),
+                                                      u.zl, u.zr, u.yl, u.yr, u.xl, u.xr))
+                fp.truncate(SOLUTION_HEADER_BYTES + 8 * N * nds)
+        _barrier(u, group)
+        data = np.memmap(path, dtype="<f8", mode="r+", offset=SOLUTION_HEADER_BYTES, shape=(nds, u.nz, u.ny, u.nx))
+        box = (slice(u.ks, u.ks + u.nzl), slice(u.js, u.js + u.nyl), slice(u.is_, u.is_ + u.nxl))
+        for f, scale in enumerate(_unit_scales(u)):
+            data[(f,) + box] = (w.sub[f] * scale).cpu().numpy().reshape(u.nzl, u.nyl, u.nxl)
+        if u.nchem > 0:
+            chem = w.sub[5].cpu().numpy().reshape(u.nzl, u.nyl, u.nxl, u.nchem)
+            for v in range(u.nchem):
+                data[(5 + v,) + box] = chem[..., v]
+        data.flush()
+        del data
+        _barrier(u, group)
+    except OSError:
+        return -1
+    return 0
+
+
+def read_solution(path):
+    """The whole file as ``{"time", "nchem", "n": (nx, ny, nz), "domain", <dataset name>: array[nz, ny, nx]}``
+    (what the reference's plotting scripts pull out of the HDF5 file)."""
+    import struct
+    import numpy as np
+    with open(path, "rb") as fp:
+        head = fp.read(SOLUTION_HEADER_BYTES)
+    if len(head) != SOLUTION_HEADER_BYTES or head[:8] != SOLUTION_MAGIC:
+        raise ValueError("%s is not a solution file" % path)
+    version, nchem, nx, ny, nz, t, *dom = struct.unpack("<iiqqqd6d", head[8:])
+    if version != 1:
+        raise ValueError("%s: unknown solution file version %d" % (path, version))
+    data = np.fromfile(path, dtype="<f8", offset=SOLUTION_HEADER_BYTES)
+    if data.size != (5 + nchem) * nx * ny * nz:
+        raise ValueError("%s is truncated" % path)
+    data = data.reshape(5 + nchem, nz, ny, nx)
+    out = {"time": t, "nchem": nchem, "n": (nx, ny, nz), "domain": dom}
+    out.update({name: data[f] for f, name in enumerate(dataset_names(nchem))})
+    return out
+
+
+def read_restart(iout, w, u, directory="."):
+    """``read_restart`` (io.cpp:940-1150): fill this rank's ``w`` from output-<iout>; the file must
+    hold the same grid and species count.  Returns (0, t) or (-1, None)."""
+    import os
+    import torch
+    try:
+        sol = read_solution(os.path.join(directory, solution_name(iout)))
+    except (OSError, ValueError) as e:
+        print("read_restart: %s" % e)
+        return -1, None
+    if sol["n"] != (u.nx, u.ny, u.nz) or sol["nchem"] != u.nchem:
+        print("read_restart: file holds %r with %d species, run asks for %r with %d"
+              % (sol["n"], sol["nchem"], (u.nx, u.ny, u.nz), u.nchem))
+        return -1, None
+    box = (slice(u.ks, u.ks + u.nzl), slice(u.js, u.js + u.nyl), slice(u.is_, u.is_ + u.nxl))
+    names = dataset_names(u.nchem)
+    for f, scale in enumerate(_unit_scales(u)):
+        w.sub[f].copy_(torch.from_numpy((sol[names[f]][box] / scale).reshape(-1).copy()))
+    if u.nchem > 0:
+        import numpy as np
+        chem = np.stack([sol[names[5 + v]][box] for v in range(u.nchem)], axis=-1)
+        w.sub[5].copy_(torch.from_numpy(chem.reshape(-1).copy()))
+    return 0, sol["time"]
