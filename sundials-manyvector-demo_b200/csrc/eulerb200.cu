@@ -304,6 +304,7 @@ struct eulerb200_ctx {
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
+  bool pair_sync = true;                                   // EULERB200_PAIR=0: CTA-wide barriers instead of pairwise row rendezvous
 };
 
 namespace {
@@ -359,6 +360,7 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   }
   for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
   P.slow_mode = 0;
+  P.pair_sync = 0;
   P.inv_energy_units = 1.0;
   P.et_rw = nullptr;
   P.state_flag = c->d_flag;
@@ -376,8 +378,9 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
   const KernelVariant& V = kVariants[c->variant];
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads);
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
   P.seg_len = L.seg_len;
+  P.pair_sync = L.pair ? 1 : 0;
   if (L.smem > c->max_smem_set) {
     EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     c->max_smem_set = L.smem;
@@ -573,6 +576,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMalloc(&c->d_alpha, sizeof(unsigned long long)));
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
+  if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = (atoi(ev) != 0);
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));

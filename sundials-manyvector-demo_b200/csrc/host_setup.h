@@ -136,12 +136,13 @@ struct LaunchGeom {
   int tx, ty;
   int seg_len;
   size_t smem;
+  bool pair;
 };
 
 // Tile shape: 256 threads; a full warp along x whenever the box is at least 31 cells
 // wide, otherwise the narrowest power of two that holds extent+1 faces (thin boxes such
 // as the 3-cell-wide hurricane plane then put the threads along y).
-inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256)
+inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256, bool want_pair = false)
 {
   LaunchGeom L;
   const long ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -149,6 +150,10 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   while (tx > 2 && tx / 2 >= ex + 1) tx /= 2;
   int ty = threads / tx;
   while (ty > 2 && ty / 2 >= ey + 1) ty /= 2;
+  // three flux arrays [NVAR][threads] must fit the 227 KB of shared memory a CTA can opt in to:
+  // many species (NVAR up to 64) get a flatter tile
+  const size_t smem_max = (size_t)227 * 1024, per_row = (size_t)(5 + nchem) * tx * sizeof(double);
+  while (ty > 2 && 3 * per_row * ty > smem_max) ty--;
   L.tx = tx; L.ty = ty;
   L.gx = (unsigned)((ex + tx - 2) / (tx - 1));
   L.gy = (unsigned)((ey + ty - 2) / (ty - 1));
@@ -159,7 +164,10 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   nseg = std::max(1L, std::min(nseg, (ez + 7) / 8));
   L.seg_len = (int)((ez + nseg - 1) / nseg);
   L.gz = (unsigned)((ez + L.seg_len - 1) / L.seg_len);
-  L.smem = (size_t)3 * (5 + nchem) * tx * ty * sizeof(double);
+  // pairwise row rendezvous (rhs_fused_kernel): rows must be warps, one named barrier per row
+  // pair (ids 1..15), and the second FY buffer has to fit the 227 KB a CTA can have
+  L.pair = want_pair && tx == 32 && ty >= 2 && ty <= 15 && 4 * per_row * ty <= smem_max;
+  L.smem = (L.pair ? 4 : 3) * per_row * ty;
   return L;
 }
 

@@ -60,6 +60,7 @@ struct RhsParams {
   // rebuilt from the gas energy carried as the LAST chemistry species,
   //   et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho)            (:1033-1042, written into w)
   // and afterwards  chemdot[nchem-1] = etdot,  etdot = 0        (:1059-1068).
+  int pair_sync;                      // rows of the tile rendezvous pairwise (see rhs_fused_kernel)
   int slow_mode;
   double inv_energy_units;
   double* et_rw;            // w[4] again, writable, for the rebuild (slow mode only)
@@ -262,8 +263,25 @@ __global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2
   }
 }
 
+#if defined(__CUDACC__)
+// named barrier: `count` threads (whole warps) meet at hardware barrier `id` (1..15)
+__device__ __forceinline__ void eb_bar_sync(int id, int count)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+#endif
+
 // Dynamic shared memory: three arrays [NVAR][T] of doubles: FX, FY (exchanged with the
 // +x / +y neighbour thread) and ZLO (thread-private: flux through the z-face below).
+//
+// Synchronisation.  Default: two CTA-wide barriers per plane (fluxes published / consumed).
+// With P.pair_sync (tile rows are warps, TX == 32): FX never leaves the warp (lane l reads lane
+// l+1's slot) and FY of row ty is read only by row ty-1, so each row meets just its two
+// neighbours once per plane on named barriers (id ty with the row below, id ty+1 with the row
+// above, 64 threads each) and FY is double-buffered (four arrays): row ty+1 can only overwrite a
+// buffer after the NEXT rendezvous, which row ty reaches after it has consumed the buffer.
+// Rows then drift apart by up to a phase per hop instead of all waiting for the slowest twice per
+// plane, so their load bursts and FP64 stretches overlap.
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
@@ -271,9 +289,11 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
   const int nv = 5 + P.nchem;
+  const bool pair = P.pair_sync != 0;
   double* FX = smem + t;
   double* FY = smem + (long)nv * T + t;
-  double* ZLO = smem + 2L * nv * T + t;
+  long fy_flip = pair ? (long)nv * T : 0;           // signed distance to the other FY buffer
+  double* ZLO = smem + (pair ? 3L : 2L) * nv * T + t;
 
   const long ti0 = P.lo[0] + (long)blockIdx.x * (TX - 1);
   const long tj0 = P.lo[1] + (long)blockIdx.y * (TY - 1);
@@ -306,7 +326,12 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     }
     if (need_y)
       face_dispatch(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
-    __syncthreads();
+    if (pair) {
+      if (ty > 0) eb_bar_sync(ty, 64);
+      if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
+    } else {
+      __syncthreads();
+    }
 
     // ---- phase B: z-face above cell (i,j,k); each flux closes the divergence of its
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
@@ -331,7 +356,13 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
                       }
                     });
     }
-    __syncthreads();
+    if (pair) {
+      __syncwarp();                 // FX of this plane consumed before the warp overwrites it
+      FY += fy_flip;
+      fy_flip = -fy_flip;
+    } else {
+      __syncthreads();
+    }
   }
 
   if (mask) atomicOr(P.state_flag, mask);

@@ -8,10 +8,11 @@
 // It proves nothing about performance and is not a fallback: the product library
 // (libeulerb200.so) contains no host path and fails loudly without a device.
 //
-// Model: one CTA at a time; each CUDA thread is a ucontext fiber; __syncthreads()
-// yields to a round-robin scheduler that resumes the fibers once all of them have
-// arrived (or exited).  threadIdx/blockIdx/blockDim/gridDim are plain globals that
-// the scheduler rewrites on every switch.
+// Model: one CTA at a time; each CUDA thread is a ucontext fiber.  Barriers (__syncthreads,
+// the named "bar.sync id, count" the kernel uses between neighbouring warp rows, __syncwarp)
+// count arrivals; a fiber that is not the last to arrive yields to a round-robin scheduler
+// until the barrier's generation changes.  threadIdx/blockIdx/blockDim/gridDim are plain
+// globals that the scheduler rewrites on every switch.
 // ---------------------------------------------------------------------------
 #pragma once
 #include <ucontext.h>
@@ -46,6 +47,21 @@ inline ucontext_t& sched_ctx() { static ucontext_t c; return c; }
 
 inline void yield_to_scheduler() { swapcontext(&fibers()[current()].ctx, &sched_ctx()); }
 
+// slots 0..15: the hardware's named barriers (0 = __syncthreads); 16 + w: __syncwarp of warp w
+struct Barrier { int arrived; unsigned gen; };
+inline std::vector<Barrier>& barriers() { static std::vector<Barrier> b; return b; }
+inline void barrier_wait(int slot, int count)
+{
+  Barrier& b = barriers()[slot];
+  const unsigned g = b.gen;
+  if (++b.arrived >= count) { b.arrived = 0; b.gen++; return; }
+  long spins = 0;
+  while (barriers()[slot].gen == g) {
+    if (++spins > 100000000L) { fprintf(stderr, "cuda_emu: barrier %d never completes (deadlock)\n", slot); abort(); }
+    yield_to_scheduler();
+  }
+}
+
 template <class Kernel, class Params> struct Launch {
   static Kernel kernel;
   static const Params* params;
@@ -72,6 +88,7 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
         memset(smem.data(), 0xFF, smem.size());       // poison: NaNs if read before written
         shared_base() = smem.data();
         fibers().assign(T, Fiber());
+        barriers().assign(16 + (T + 31) / 32, Barrier{0, 0u});
         for (int t = 0; t < T; t++) {
           Fiber& f = fibers()[t];
           f.done = false;
@@ -82,7 +99,7 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
           f.ctx.uc_link = &sched_ctx();
           makecontext(&f.ctx, (void (*)())L::entry, 0);
         }
-        // each pass resumes every live fiber once: from one barrier to the next
+        // each pass resumes every live fiber once, until it blocks in a barrier again or exits
         // (alternating the order between passes makes a missing barrier show up as wrong data)
         bool any = true;
         int pass = 0;
@@ -110,5 +127,12 @@ template <class F> void launch_aux_like(F f, long n) { for (long c = 0; c < n; c
 #define gridDim (cuda_emu::gdim())
 #define EB_DYN_SMEM(type, name) type* name = (type*)cuda_emu::shared_base()
 
-inline void __syncthreads() { cuda_emu::yield_to_scheduler(); }
+inline int emu_block_threads() { return (int)(cuda_emu::bdim().x * cuda_emu::bdim().y * cuda_emu::bdim().z); }
+inline void __syncthreads() { cuda_emu::barrier_wait(0, emu_block_threads()); }
+inline void eb_bar_sync(int id, int count) { cuda_emu::barrier_wait(id, count); }
+inline void __syncwarp()
+{
+  const int T = emu_block_threads(), w = cuda_emu::current() / 32;
+  cuda_emu::barrier_wait(16 + w, (T - 32 * w < 32) ? T - 32 * w : 32);
+}
 inline int atomicOr(int* addr, int v) { int old = *addr; *addr = old | v; return old; }

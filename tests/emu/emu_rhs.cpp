@@ -8,7 +8,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units)
+                       int threads, int use_aux, double energy_units, int pair)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -44,7 +44,9 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.state_flag = &flag;
   const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};
   for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
-  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads);
+  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads, pair != 0);
+  P.pair_sync = L.pair ? 1 : 0;
+  if (pair == 2 && !L.pair) return -77;           // the caller insisted on the pairwise path
   P.seg_len = L.seg_len;
   cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
   *state_bits = flag;

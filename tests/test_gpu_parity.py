@@ -28,7 +28,26 @@ CASES = [
     ((200, 3, 3), 0, [N] * 6),            # sod_x shape
     ((3, 3, 50), 2, [P, P, P, P, N, N]),
     ((5, 4, 3), 2, [P] * 6),
+    ((40, 26, 12), 24, [R, R, P, P, N, N]),   # NVAR = 29: the tile is flattened to fit 227 KB of shared memory
 ]
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_row_synchronisation_modes_agree_bitwise(pkg, oracle_mod, monkeypatch, pair):
+    """EULERB200_PAIR=1 (default: neighbouring warp rows meet on named barriers, FY double-buffered)
+    and =0 (two CTA-wide barriers per plane) differ only in synchronisation: identical bits."""
+    n, nchem, bcs = (70, 50, 24), 10, [R] * 6
+    parts = oracle_mod.random_state(n, nchem, seed=11)
+    outs = []
+    for mode in (pair, "0"):
+        monkeypatch.setenv("EULERB200_PAIR", mode)
+        u = make_udata(pkg, n, nchem, bcs)
+        ret, got = gpu_feuler(pkg, u, parts)
+        assert ret == 0, u.last_error()
+        outs.append(got)
+        u.FreeData()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("n,nchem,bcs", CASES)

@@ -31,6 +31,7 @@ def nbr_single(bcs):
     ((40, 3, 3), 0, [N] * 6, 256),           # sod_x shape
     ((7, 6, 26), 4, [R, R, P, P, N, N], 64), # several z-segments
     ((70, 12, 10), 2, [P] * 6, 128),         # interior CTAs: the no-ghost path reading aux arrays
+    ((33, 9, 4), 24, [N] * 6, 384),          # NVAR = 29: the tile is flattened to fit shared memory
 ])
 def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, threads):
     w = oracle_mod.random_state(n, nchem, seed=sum(n))
@@ -44,6 +45,30 @@ def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, th
     # same answer with every derived value computed on the fly (no aux arrays)
     ret, got2, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, use_aux=0)
     assert ret == 0 and max(normwise_errors(got2, ref, floor)) <= 1e-12
+
+
+@pytest.mark.parametrize("n,nchem,bcs,threads", [
+    ((70, 12, 10), 2, [P] * 6, 128),          # 4 rows per tile, interior and ghost CTAs
+    ((35, 25, 9), 0, [P, P, R, R, N, N], 384),  # 12 rows: the production tile shape, two tiles along y
+    ((33, 5, 26), 10, [R] * 6, 64),           # 2 rows (one real + the face-only row), several z-segments
+])
+def test_emulated_pairwise_row_rendezvous(emu, oracle_mod, port, n, nchem, bcs, threads):
+    """EULERB200_PAIR path: neighbouring warp rows meet on named barriers, FY double-buffered.
+    The emulator schedules fibres barrier by barrier in alternating order, so a missing or
+    mis-paired rendezvous shows up as poisoned (NaN) or stale fluxes.  Bit-identical to the
+    CTA-wide-barrier path: only the synchronisation differs."""
+    w = oracle_mod.random_state(n, nchem, seed=7 + sum(n))
+    d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+    ret, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads)
+    ret2, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads, pair=2)
+    assert ret == 0 and ret2 == 0
+    for a, b in zip(base, got):
+        assert (a is None and b is None) or np.array_equal(a, b)
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+    assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
+    # thin boxes (rows are not warps) silently keep the CTA-wide barriers
+    assert emu.rhs((3, 20, 17), 0, d, 1.4, [N] * 6, nbr_single([N] * 6), 0,
+                   oracle_mod.random_state((3, 20, 17), 0, seed=1), threads=256, pair=2)[0] == -77
 
 
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):

@@ -16,12 +16,14 @@ ap.add_argument("--n", type=int, nargs=3, default=[256, 256, 256])
 ap.add_argument("--nchem", type=int, nargs="+", default=[10, 0])
 ap.add_argument("--variants", type=int, nargs="+", default=[0, 1, 2, 3])
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--pair", type=int, nargs="+", default=[0], help="EULERB200_PAIR values to time")
 args = ap.parse_args()
 build()
 pkg = load_package()
 for nchem in args.nchem:
-    for v in args.variants:
+    for v, pair in [(v, q) for v in args.variants for q in args.pair]:
         os.environ["EULERB200_VARIANT"] = str(v)
+        os.environ["EULERB200_PAIR"] = str(pair)
         u = pkg.EulerData(nchem=nchem)
         u.nx, u.ny, u.nz = args.n
         u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = pkg.BC_REFLECTING
@@ -40,8 +42,8 @@ for nchem in args.nchem:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         cells = u.nx * u.ny * u.nz
-        print("n=%s nchem=%2d variant=%d  %8.3f ms  %6.3f Gcell/s  checksum=%.12e"
-              % (args.n, nchem, v, ms, cells / ms / 1e6, float(wdot.sub[0].double().abs().sum())), flush=True)
+        print("n=%s nchem=%2d variant=%d pair=%d  %8.3f ms  %6.3f Gcell/s  checksum=%.12e"
+              % (args.n, nchem, v, pair, ms, cells / ms / 1e6, float(wdot.sub[0].double().abs().sum())), flush=True)
         u.FreeData()
         del w, wdot
         torch.cuda.empty_cache()
