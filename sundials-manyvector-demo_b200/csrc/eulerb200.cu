@@ -300,11 +300,11 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set = 0;
+  size_t max_smem_set = 0, carveout_for = (size_t)-1;
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
-  bool pair_sync = true;                                   // EULERB200_PAIR=0: CTA-wide barriers instead of pairwise row rendezvous
+  int pair_sync = 2;                                       // EULERB200_PAIR: 0 CTA-wide barriers, 1/2 pairwise row rendezvous (rhs_kernel.cuh)
 };
 
 namespace {
@@ -380,10 +380,17 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
   const KernelVariant& V = kVariants[c->variant];
   const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
   P.seg_len = L.seg_len;
-  P.pair_sync = L.pair ? 1 : 0;
+  P.pair_sync = L.pair;
   if (L.smem > c->max_smem_set) {
     EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     c->max_smem_set = L.smem;
+  }
+  if (L.smem != c->carveout_for) {
+    // the stencil loads live in L1: ask for the smallest shared-memory carve-out that holds one CTA
+    // (+1 KB the system reserves per CTA) and leave the rest of the 256 KB to L1
+    const int pct = (int)std::min<size_t>(100, (100 * (L.smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    c->carveout_for = L.smem;
   }
   V.fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
   c->launches++;
@@ -576,7 +583,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMalloc(&c->d_alpha, sizeof(unsigned long long)));
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
-  if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = (atoi(ev) != 0);
+  if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));

@@ -271,15 +271,19 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 }
 #endif
 
-// Dynamic shared memory: three arrays [NVAR][T] of doubles: FX, FY (exchanged with the
-// +x / +y neighbour thread) and ZLO (thread-private: flux through the z-face below).
+// Dynamic shared memory: FX [NVAR][T-TX], FY [NVAR][T] (exchanged with the +x / +y neighbour
+// thread) and ZLO [NVAR][T-TX] (thread-private: flux through the z-face below); 127.5 KB at
+// NVAR = 15 with 384 threads, which leaves the SM its 132 KB carve-out and 124 KB of L1 -- the
+// stencil loads live in L1, and its size shows directly in the kernel time.
 //
 // Synchronisation.  Default: two CTA-wide barriers per plane (fluxes published / consumed).
 // With P.pair_sync (tile rows are warps, TX == 32): FX never leaves the warp (lane l reads lane
 // l+1's slot) and FY of row ty is read only by row ty-1, so each row meets just its two
 // neighbours once per plane on named barriers (id ty with the row below, id ty+1 with the row
 // above, 64 threads each) and FY is double-buffered (four arrays): row ty+1 can only overwrite a
-// buffer after the NEXT rendezvous, which row ty reaches after it has consumed the buffer.
+// buffer after the NEXT rendezvous, which row ty reaches after it has consumed the buffer
+// (pair_sync == 2: one FY buffer and a second rendezvous per plane instead, when the fourth
+// array does not fit).
 // Rows then drift apart by up to a phase per hop instead of all waiting for the slowest twice per
 // plane, so their load bursts and FP64 stretches overlap.
 template <int MAXT, int MINB>
@@ -290,10 +294,13 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
   const int nv = 5 + P.nchem;
   const bool pair = P.pair_sync != 0;
+  const bool two_fy = P.pair_sync == 1;
+  // the face-only top row of the tile never touches FX / ZLO: those arrays are [NVAR][TR]
+  const int TR = T - TX;
   double* FX = smem + t;
-  double* FY = smem + (long)nv * T + t;
-  long fy_flip = pair ? (long)nv * T : 0;           // signed distance to the other FY buffer
-  double* ZLO = smem + (pair ? 3L : 2L) * nv * T + t;
+  double* FY = smem + (long)nv * TR + t;
+  long fy_flip = two_fy ? (long)nv * T : 0;         // signed distance to the other FY buffer
+  double* ZLO = smem + (long)nv * (TR + (two_fy ? 2L : 1L) * T) + t;
 
   const long ti0 = P.lo[0] + (long)blockIdx.x * (TX - 1);
   const long tj0 = P.lo[1] + (long)blockIdx.y * (TY - 1);
@@ -316,12 +323,12 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   // z-face below the first plane of the segment
   if (owns)
     face_dispatch(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
-                  [&](int v, double x) { ZLO[v * T] = x; });
+                  [&](int v, double x) { ZLO[v * TR] = x; });
 
   for (long k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (need_x) {
-      const int bits = face_dispatch(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * T] = x; });
+      const int bits = face_dispatch(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
       if (owns) mask |= bits;
     }
     if (need_y)
@@ -339,10 +346,10 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
       const long cell = i + P.nx * (j + P.ny * k);
       face_dispatch(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
                     [&](int v, double zup) {
-                      const double div = ((FX[v * T + 1] - FX[v * T]) * P.rdx
+                      const double div = ((FX[v * TR + 1] - FX[v * TR]) * P.rdx
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)
-                                        + (zup - ZLO[v * T]) * P.rdz;
-                      ZLO[v * T] = zup;
+                                        + (zup - ZLO[v * TR]) * P.rdz;
+                      ZLO[v * TR] = zup;
                       if (!P.slow_mode) {
                         if (v < 5) P.wdot[v][cell] = P.forcing[v] - div;
                         else P.wdot[5][cell * P.nchem + (v - 5)] = 0.0 - div;
@@ -356,10 +363,13 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
                       }
                     });
     }
-    if (pair) {
+    if (two_fy) {
       __syncwarp();                 // FX of this plane consumed before the warp overwrites it
       FY += fy_flip;
       fy_flip = -fy_flip;
+    } else if (pair) {              // single FY buffer: a second rendezvous releases it
+      if (ty > 0) eb_bar_sync(ty, 64);
+      if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
     } else {
       __syncthreads();
     }

@@ -44,9 +44,9 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.state_flag = &flag;
   const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};
   for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
-  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads, pair != 0);
-  P.pair_sync = L.pair ? 1 : 0;
-  if (pair == 2 && !L.pair) return -77;           // the caller insisted on the pairwise path
+  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads, pair);
+  P.pair_sync = L.pair;
+  if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
   P.seg_len = L.seg_len;
   cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
   *state_bits = flag;

@@ -32,10 +32,11 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("pair", ["1", "2"])
 def test_row_synchronisation_modes_agree_bitwise(pkg, oracle_mod, monkeypatch, pair):
-    """EULERB200_PAIR=1 (default: neighbouring warp rows meet on named barriers, FY double-buffered)
-    and =0 (two CTA-wide barriers per plane) differ only in synchronisation: identical bits."""
+    """EULERB200_PAIR=2 (default: neighbouring warp rows meet on named barriers twice per plane), =1
+    (once per plane, FY double-buffered) and =0 (two CTA-wide barriers per plane) differ only in
+    synchronisation: identical bits."""
     n, nchem, bcs = (70, 50, 24), 10, [R] * 6
     parts = oracle_mod.random_state(n, nchem, seed=11)
     outs = []

@@ -60,10 +60,11 @@ def test_emulated_pairwise_row_rendezvous(emu, oracle_mod, port, n, nchem, bcs, 
     w = oracle_mod.random_state(n, nchem, seed=7 + sum(n))
     d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
     ret, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads)
-    ret2, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads, pair=2)
-    assert ret == 0 and ret2 == 0
-    for a, b in zip(base, got):
-        assert (a is None and b is None) or np.array_equal(a, b)
+    for mode in (1, 2):           # two FY buffers / one buffer and a second rendezvous
+        ret2, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads, pair=mode)
+        assert ret == 0 and ret2 == 0
+        for a, b in zip(base, got):
+            assert (a is None and b is None) or np.array_equal(a, b)
     ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
     assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
     # thin boxes (rows are not warps) silently keep the CTA-wide barriers
