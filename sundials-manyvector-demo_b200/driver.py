@@ -4,7 +4,9 @@ Stands in for what ``euler3D_main.cpp:191-417`` asks of ARKODE's ARKStep in the 
 runs of the reference (sod, linear_advection, rayleigh_taylor, hurricane, fluid_blast):
 
 * embedded explicit Runge-Kutta step with the tables ARKODE uses by default for
-  ``order`` 2/3/4 (Heun-Euler 2-1-2, Bogacki-Shampine 4-2-3, Zonneveld 5-3-4),
+  ``order`` 2/3/4/5 (Heun-Euler 2-1-2, Bogacki-Shampine 4-2-3, Zonneveld 5-3-4, Cash-Karp 6-4-5),
+  or a table chosen by its ``etable`` id when ``order = 0`` (also Fehlberg 6-4-5,
+  Dormand-Prince 7-4-5, Knoth-Wolke 3-3),
 * WRMS error norm with scalar tolerances (``ARKStepSStolerances``), PID step controller
   with ARKODE's default constants, error-test failures, optional fixed step,
 * the CFL hook (``ARKStepSetStabilityFn(stability)``, used when ``cfl > 0``),
@@ -25,13 +27,51 @@ import ctypes as C
 import math
 
 # (A rows, b, b_embedded, method order p, embedding order q)
-TABLES = {
-    2: ([[], [1.0]], [0.5, 0.5], [1.0, 0.0], 2, 1),                                    # Heun-Euler 2-1-2
-    3: ([[], [0.5], [0.0, 0.75], [2.0 / 9, 1.0 / 3, 4.0 / 9]],                          # Bogacki-Shampine 4-2-3
-        [2.0 / 9, 1.0 / 3, 4.0 / 9, 0.0], [7.0 / 24, 0.25, 1.0 / 3, 0.125], 3, 2),
-    4: ([[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0], [5.0 / 32, 7.0 / 32, 13.0 / 32, -1.0 / 32]],  # Zonneveld 5-3-4
-        [1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6, 0.0], [-0.5, 7.0 / 3, 7.0 / 3, 13.0 / 6, -16.0 / 3], 4, 3),
-}
+HEUN_EULER = ([[], [1.0]], [0.5, 0.5], [1.0, 0.0], 2, 1)
+BOGACKI_SHAMPINE = ([[], [0.5], [0.0, 0.75], [2.0 / 9, 1.0 / 3, 4.0 / 9]],
+                    [2.0 / 9, 1.0 / 3, 4.0 / 9, 0.0], [7.0 / 24, 0.25, 1.0 / 3, 0.125], 3, 2)
+ZONNEVELD = ([[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0], [5.0 / 32, 7.0 / 32, 13.0 / 32, -1.0 / 32]],
+             [1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6, 0.0], [-0.5, 7.0 / 3, 7.0 / 3, 13.0 / 6, -16.0 / 3], 4, 3)
+CASH_KARP = ([[], [1.0 / 5], [3.0 / 40, 9.0 / 40], [3.0 / 10, -9.0 / 10, 6.0 / 5],
+              [-11.0 / 54, 5.0 / 2, -70.0 / 27, 35.0 / 27],
+              [1631.0 / 55296, 175.0 / 512, 575.0 / 13824, 44275.0 / 110592, 253.0 / 4096]],
+             [37.0 / 378, 0.0, 250.0 / 621, 125.0 / 594, 0.0, 512.0 / 1771],
+             [2825.0 / 27648, 0.0, 18575.0 / 48384, 13525.0 / 55296, 277.0 / 14336, 0.25], 5, 4)
+FEHLBERG = ([[], [0.25], [3.0 / 32, 9.0 / 32], [1932.0 / 2197, -7200.0 / 2197, 7296.0 / 2197],
+             [439.0 / 216, -8.0, 3680.0 / 513, -845.0 / 4104],
+             [-8.0 / 27, 2.0, -3544.0 / 2565, 1859.0 / 4104, -11.0 / 40]],
+            [16.0 / 135, 0.0, 6656.0 / 12825, 28561.0 / 56430, -9.0 / 50, 2.0 / 55],
+            [25.0 / 216, 0.0, 1408.0 / 2565, 2197.0 / 4104, -0.2, 0.0], 5, 4)
+DORMAND_PRINCE = ([[], [0.2], [3.0 / 40, 9.0 / 40], [44.0 / 45, -56.0 / 15, 32.0 / 9],
+                   [19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729],
+                   [9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656],
+                   [35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84]],
+                  [35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0.0],
+                  [5179.0 / 57600, 0.0, 7571.0 / 16695, 393.0 / 640, -92097.0 / 339200, 187.0 / 2100, 1.0 / 40], 5, 4)
+KNOTH_WOLKE = ([[], [1.0 / 3], [-3.0 / 16, 15.0 / 16]], [1.0 / 6, 3.0 / 10, 8.0 / 15], None, 3, 0)   # no embedding
+
+# ARKStepSetOrder(order): ARKODE's default explicit table of that order
+TABLES = {2: HEUN_EULER, 3: BOGACKI_SHAMPINE, 4: ZONNEVELD, 5: CASH_KARP}
+# ARKStepSetTableNum(.., etable): ARKODE_ERKTableID values (arkode_butcher_erk.h, SUNDIALS 6.2) for
+# the tables whose coefficients are public textbook material.  The additive-method explicit parts
+# (2, 4, 9, 13 = ARK437L2SA, 14), Sayfy-Aburub (5), Verner (10) and Fehlberg 13-7-8 (11) are not
+# restated: the blast input files (etable = 13) run with order = 4 instead (inputs/*.txt).
+TABLES_BY_ID = {0: HEUN_EULER, 1: BOGACKI_SHAMPINE, 3: ZONNEVELD, 6: CASH_KARP, 7: FEHLBERG,
+                8: DORMAND_PRINCE, 12: KNOTH_WOLKE}
+ERK_NONE = -1
+
+
+def select_table(order, etable=ERK_NONE):
+    """'order' overrides 'etable' (euler3D_main.cpp:207-213); order 0 and no table: order 4."""
+    if order != 0:
+        if order not in TABLES:
+            raise ValueError("explicit tables are provided for order 2, 3, 4 and 5")
+        return TABLES[order]
+    if etable == ERK_NONE:
+        return TABLES[4]
+    if etable not in TABLES_BY_ID:
+        raise ValueError("ERK table id %d is not provided (have %s)" % (etable, sorted(TABLES_BY_ID)))
+    return TABLES_BY_ID[etable]
 
 
 class ARKODEParameters:
@@ -39,6 +79,7 @@ class ARKODEParameters:
 
     def __init__(self, **kw):
         self.order = 4
+        self.etable = ERK_NONE
         self.rtol, self.atol = 1e-8, 1e-12
         self.fixedstep = 0
         self.h0 = self.hmin = self.hmax = 0.0
@@ -107,9 +148,9 @@ class ERKStep:
     def __init__(self, ops, t0, w, opts=None, cfl=0.0):
         self.ops, self.t, self.w = ops, float(t0), w
         self.o = opts or ARKODEParameters()
-        if self.o.order not in TABLES:
-            raise ValueError("explicit tables are provided for order 2, 3 and 4")
-        self.A, self.b, self.bhat, self.p, self.q = TABLES[self.o.order]
+        self.A, self.b, self.bhat, self.p, self.q = select_table(self.o.order, self.o.etable)
+        if self.bhat is None and not self.o.fixedstep:
+            raise ValueError("this table has no embedding: it needs fixedstep = 1")
         self.cfl = cfl
         s = len(self.b)
         self.k = [ops.new_like(w) for _ in range(s)]

@@ -117,3 +117,86 @@ def test_fluid_blast_initial_condition_matches_reference(pkg):
     # the generator itself: first draws of std::mt19937_64(5489) are 14514284786278117030, 4620546740167642908
     g = pkg.problems.MT19937_64(5489)
     assert g.next() == 14514284786278117030 and g.next() == 4620546740167642908
+
+
+class _OdeOps:
+    """VecOps on a 2-component numpy vector with y' = (-y0^2 + sin t, y0 y1): enough to
+    observe the order of a Runge-Kutta table without the fluid RHS."""
+
+    def new_like(self, w):
+        from helpers import NpVec
+        return NpVec([np.empty_like(s) for s in w.sub])
+
+    def lincomb(self, out, coefs, vecs):
+        acc = sum(c * v.sub[0] for c, v in zip(coefs, vecs))
+        out.sub[0][...] = acc
+
+    def wrms(self, x, y, rtol, atol):
+        q = x.sub[0] / (rtol * np.abs(y.sub[0]) + atol)
+        return float(np.sqrt(np.mean(q * q)))
+
+    def rhs(self, t, w, wdot):
+        y = w.sub[0]
+        wdot.sub[0][...] = [-y[0] * y[0] + np.sin(t), y[0] * y[1]]
+        return 0
+
+
+def _order_residuals(A, b):
+    """Rooted-tree order conditions up to order 5 (17 of them); returns {order: max residual}."""
+    s = len(b)
+    M = np.zeros((s, s))
+    for i, row in enumerate(A):
+        M[i, :len(row)] = row
+    b = np.asarray(b, dtype=float)
+    c = M.sum(axis=1)
+    Ac, Ac2, Ac3, AAc, AAc2, AAAc = M @ c, M @ c**2, M @ c**3, M @ (M @ c), M @ (M @ c**2), M @ (M @ (M @ c))
+    cond = {1: [(b.sum(), 1.0)], 2: [(b @ c, 1 / 2)], 3: [(b @ c**2, 1 / 3), (b @ Ac, 1 / 6)],
+            4: [(b @ c**3, 1 / 4), (b @ (c * Ac), 1 / 8), (b @ Ac2, 1 / 12), (b @ AAc, 1 / 24)],
+            5: [(b @ c**4, 1 / 5), (b @ (c**2 * Ac), 1 / 10), (b @ (Ac * Ac), 1 / 20), (b @ (c * Ac2), 1 / 15),
+                (b @ Ac3, 1 / 20), (b @ (c * AAc), 1 / 30), (b @ (M @ (c * Ac)), 1 / 40), (b @ AAc2, 1 / 60),
+                (b @ AAAc, 1 / 120)]}
+    return {p: max(abs(x - y) for x, y in v) for p, v in cond.items()}
+
+
+@pytest.mark.parametrize("tid", [0, 1, 3, 6, 7, 8, 12])
+def test_erk_tables_by_id_satisfy_their_order_conditions(pkg, tid):
+    """ARKStepSetTableNum ids (euler3D_main.cpp:211-212): the method has order p, the
+    embedding order q -- and not one more."""
+    A, b, bhat, p, q = pkg.driver.TABLES_BY_ID[tid]
+    res = _order_residuals(A, b)
+    assert all(res[o] < 1e-14 for o in range(1, p + 1)), res
+    assert p == 5 or res[p + 1] > 1e-6
+    if bhat is not None:
+        rh = _order_residuals(A, bhat)
+        assert all(rh[o] < 1e-14 for o in range(1, q + 1)), rh
+        assert rh[q + 1] > 1e-6
+
+
+@pytest.mark.parametrize("tid", [3, 6, 8, 12])
+def test_erk_tables_observed_order(pkg, tid):
+    from helpers import NpVec
+    p = pkg.driver.TABLES_BY_ID[tid][3]
+    sols = []
+    for h in (0.1, 0.05, 0.025):
+        opts = pkg.driver.ARKODEParameters(order=0, etable=tid, fixedstep=1, hmax=h)
+        step = pkg.driver.ERKStep(_OdeOps(), 0.0, NpVec([np.array([0.5, 1.0])]), opts)
+        ret, t = step.evolve(1.0)
+        assert ret == 0 and t == 1.0
+        sols.append(step.w.sub[0].copy())
+    opts = pkg.driver.ARKODEParameters(order=0, etable=8, rtol=1e-13, atol=1e-14)
+    ref = pkg.driver.ERKStep(_OdeOps(), 0.0, NpVec([np.array([0.5, 1.0])]), opts)
+    assert ref.evolve(1.0)[0] == 0
+    errs = [np.abs(s - ref.w.sub[0]).max() for s in sols]
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert min(rates) > p - 0.5, (errs, rates)
+
+
+def test_order_overrides_etable_and_unknown_ids_are_refused(pkg):
+    d = pkg.driver
+    assert d.select_table(4, 8) is d.ZONNEVELD           # "order" overrides "etable"
+    assert d.select_table(0, 8) is d.DORMAND_PRINCE
+    assert d.select_table(0) is d.ZONNEVELD
+    with pytest.raises(ValueError):
+        d.select_table(0, 13)                             # ARK437L2SA's explicit part: not provided
+    with pytest.raises(ValueError):
+        d.ERKStep(_OdeOps(), 0.0, None, d.ARKODEParameters(order=0, etable=12))   # no embedding

@@ -18,7 +18,7 @@ ap.add_argument("--variants", type=int, nargs="+", default=[0, 1, 2, 3])
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--pair", type=int, nargs="+", default=[0], help="EULERB200_PAIR values to time")
 args = ap.parse_args()
-build()
+if os.environ.get("EB_TUNE_BUILD"): build()
 pkg = load_package()
 for nchem in args.nchem:
     for v, pair in [(v, q) for v in args.variants for q in args.pair]:
