@@ -322,10 +322,6 @@ const KernelVariant kVariants[] = {
     {eb::rhs_fused_kernel<384, 1>, 384, "384x1 (<=168 regs)"},
     {eb::rhs_fused_kernel<512, 1>, 512, "512x1 (<=128 regs)"},
     {eb::rhs_fused_kernel<256, 2>, 256, "256x2 (<=128 regs)"},
-    {eb::rhs_fused_kernel<384, 1, 1>, 384, "384x1, far z-stencil points bypass L1"},
-    {eb::rhs_fused_kernel<384, 1, 2>, 384, "384x1, all z-stencil points bypass L1"},
-    {eb::rhs_fused_kernel<384, 1, 4>, 384, "384x1, streaming stores of wdot"},
-    {eb::rhs_fused_kernel<384, 1, 5>, 384, "384x1, far z-stencil points bypass L1 + streaming stores"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultVariant = 1;

@@ -112,40 +112,17 @@ EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilP
   }
 }
 
-// Loads that do not allocate a line in L1 (experiment EULERB200_VARIANT=4/5): the z-stencil
-// working set of a CTA (6 planes x tile x NVAR) exceeds L1, so its far points only evict the
-// x/y-stencil lines of the current plane.
-EB_HD double ld_stream(const double* p)
-{
-#if defined(__CUDA_ARCH__)
-  double x;
-  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(x) : "l"(p));
-  return x;
-#else
-  return *p;
-#endif
-}
-EB_HD double2 ld_stream2(const double* p)
-{
-#if defined(__CUDA_ARCH__)
-  double2 x;
-  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(x.x), "=d"(x.y) : "l"(p));
-  return x;
-#else
-  return *reinterpret_cast<const double2*>(p);
-#endif
-}
 // wdot is written once and never read by this kernel: a streaming store (evict-first in L2)
-// leaves the L2 to the state lines neighbouring CTAs re-read (experiment, variants 6/7).
-template <bool CS> EB_HD void st_out(double* p, double x)
+// leaves the L2 to the state lines neighbouring CTAs re-read (-0.27 % at 512^3/NVAR=15,
+// profiles/r1g_ab_l1_hints.txt).
+EB_HD void st_out(double* p, double x)
 {
 #if defined(__CUDA_ARCH__)
-  if (CS) { __stcs(p, x); return; }
-#endif
+  __stcs(p, x);
+#else
   *p = x;
+#endif
 }
-// ZH: 0 plain loads; 1 stencil points 0,1,4,5 bypass L1; 2 all six points bypass L1
-template <int ZH> EB_HD bool stream_pt(int l) { return ZH == 2 || (ZH == 1 && (l < 2 || l > 3)); }
 
 template <bool GEN>
 EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
@@ -161,7 +138,7 @@ EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
 // handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
 // i.e. of cell (i,j,k) itself.
-template <bool GEN, int ZH, class Emit>
+template <bool GEN, class Emit>
 EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
   StencilPt pt[6];
@@ -175,14 +152,6 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   FluidStencil s;
 #pragma unroll
   for (int l = 0; l < 6; l++) {
-    if (!GEN && stream_pt<ZH>(l)) {
-      s.r[l] = ld_stream(P.w[0] + pt[l].off);
-      s.mn[l] = ld_stream(P.w[fn] + pt[l].off);
-      s.m1[l] = ld_stream(P.w[f1] + pt[l].off);
-      s.m2[l] = ld_stream(P.w[f2] + pt[l].off);
-      s.e[l] = ld_stream(P.w[4] + pt[l].off);
-      continue;
-    }
     s.r[l] = load_fluid<GEN>(P, pt[l], 0);
     s.mn[l] = load_fluid<GEN>(P, pt[l], fn);
     s.m1[l] = load_fluid<GEN>(P, pt[l], f1);
@@ -194,12 +163,6 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   if (!GEN && P.aux[0] != nullptr) {
 #pragma unroll
     for (int l = 0; l < 6; l++) {
-      if (stream_pt<ZH>(l)) {
-        s.rinv[l] = ld_stream(P.aux[0] + pt[l].off);
-        s.p[l] = ld_stream(P.aux[1] + pt[l].off);
-        s.c[l] = ld_stream(P.aux[2] + pt[l].off);
-        continue;
-      }
       s.rinv[l] = P.aux[0][pt[l].off];
       s.p[l] = P.aux[1][pt[l].off];
       s.c[l] = P.aux[2][pt[l].off];
@@ -253,14 +216,12 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     if (vec) {
       double2 c[6], cn[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++)
-        c[l] = (!GEN && stream_pt<ZH>(l)) ? ld_stream2(cp[l]) : *reinterpret_cast<const double2*>(cp[l]);
+      for (int l = 0; l < 6; l++) c[l] = *reinterpret_cast<const double2*>(cp[l]);
 #pragma unroll 1
       for (int v = 0; v < P.nchem; v += 2) {
         const int vn = (v + 2 < P.nchem) ? v + 2 : v;
 #pragma unroll
-        for (int l = 0; l < 6; l++)
-          cn[l] = (!GEN && stream_pt<ZH>(l)) ? ld_stream2(cp[l] + vn) : *reinterpret_cast<const double2*>(cp[l] + vn);
+        for (int l = 0; l < 6; l++) cn[l] = *reinterpret_cast<const double2*>(cp[l] + vn);
         double a[6], b[6];
 #pragma unroll
         for (int l = 0; l < 6; l++) {
@@ -287,10 +248,10 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   return bits;
 }
 
-template <int ZH = 0, class Emit>
+template <class Emit>
 EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
-  return gen ? face_all<true, 0>(P, dir, i, j, k, emit) : face_all<false, ZH>(P, dir, i, j, k, emit);
+  return gen ? face_all<true>(P, dir, i, j, k, emit) : face_all<false>(P, dir, i, j, k, emit);
 }
 
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
@@ -337,11 +298,9 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // array does not fit).
 // Rows then drift apart by up to a phase per hop instead of all waiting for the slowest twice per
 // plane, so their load bursts and FP64 stretches overlap.
-template <int MAXT, int MINB, int OPT = 0>
+template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
-  constexpr int ZH = OPT & 3;            // z-stencil loads that bypass L1 (see stream_pt)
-  constexpr bool CS = (OPT & 4) != 0;    // streaming stores of wdot
   EB_DYN_SMEM(double, smem);
   const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
@@ -375,7 +334,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
   // z-face below the first plane of the segment
   if (owns)
-    face_dispatch<ZH>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
+    face_dispatch(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
                   [&](int v, double x) { ZLO[v * TR] = x; });
 
   for (long k = k0; k < k1; k++) {
@@ -397,22 +356,22 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
     if (owns) {
       const long cell = i + P.nx * (j + P.ny * k);
-      face_dispatch<ZH>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
+      face_dispatch(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
                     [&](int v, double zup) {
                       const double div = ((FX[v * TR + 1] - FX[v * TR]) * P.rdx
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)
                                         + (zup - ZLO[v * TR]) * P.rdz;
                       ZLO[v * TR] = zup;
                       if (!P.slow_mode) {
-                        if (v < 5) st_out<CS>(P.wdot[v] + cell, P.forcing[v] - div);
-                        else st_out<CS>(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
+                        if (v < 5) st_out(P.wdot[v] + cell, P.forcing[v] - div);
+                        else st_out(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
                       } else if (v == 4) {          // etdot goes to the gas-energy species
-                        st_out<CS>(P.wdot[5] + cell * P.nchem + (P.nchem - 1), P.forcing[4] - div);
-                        st_out<CS>(P.wdot[4] + cell, 0.0);
+                        st_out(P.wdot[5] + cell * P.nchem + (P.nchem - 1), P.forcing[4] - div);
+                        st_out(P.wdot[4] + cell, 0.0);
                       } else if (v < 4) {
-                        st_out<CS>(P.wdot[v] + cell, P.forcing[v] - div);
+                        st_out(P.wdot[v] + cell, P.forcing[v] - div);
                       } else if (v < 4 + P.nchem) {  // every species but the last (overwritten above)
-                        st_out<CS>(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
+                        st_out(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
                       }
                     });
     }

@@ -30,6 +30,7 @@
 #include <vector>
 #include "eulerb200.h"
 #include "problems.hpp"
+#include "erk_tables.hpp"
 
 namespace {
 
@@ -79,32 +80,10 @@ Vec new_vec(long N, int nchem)
 }
 void free_vec(Vec& v) { for (int f = 0; f < v.nsub; f++) eulerb200_device_free(v.sub[f]); }
 
-// embedded explicit Runge-Kutta tables: ARKODE's defaults for order 2, 3, 4
-struct Table { int s, p, q; double A[5][5], b[5], bh[5]; };
-Table make_table(int order)
-{
-  Table T;
-  memset(&T, 0, sizeof T);
-  if (order == 2) { T.s = 2; T.p = 2; T.q = 1; T.A[1][0] = 1.0; T.b[0] = T.b[1] = 0.5; T.bh[0] = 1.0; }
-  else if (order == 3) {
-    T.s = 4; T.p = 3; T.q = 2;
-    T.A[1][0] = 0.5; T.A[2][1] = 0.75; T.A[3][0] = 2.0 / 9; T.A[3][1] = 1.0 / 3; T.A[3][2] = 4.0 / 9;
-    T.b[0] = 2.0 / 9; T.b[1] = 1.0 / 3; T.b[2] = 4.0 / 9;
-    T.bh[0] = 7.0 / 24; T.bh[1] = 0.25; T.bh[2] = 1.0 / 3; T.bh[3] = 0.125;
-  } else {
-    T.s = 5; T.p = 4; T.q = 3;
-    T.A[1][0] = 0.5; T.A[2][1] = 0.5; T.A[3][2] = 1.0;
-    T.A[4][0] = 5.0 / 32; T.A[4][1] = 7.0 / 32; T.A[4][2] = 13.0 / 32; T.A[4][3] = -1.0 / 32;
-    T.b[0] = 1.0 / 6; T.b[1] = 1.0 / 3; T.b[2] = 1.0 / 3; T.b[3] = 1.0 / 6;
-    T.bh[0] = -0.5; T.bh[1] = 7.0 / 3; T.bh[2] = 7.0 / 3; T.bh[3] = 13.0 / 6; T.bh[4] = -16.0 / 3;
-  }
-  return T;
-}
-
 struct Stepper {
   eulerb200_ctx* ctx;
   Table T;
-  Vec w, ytmp, yerr, k[5];
+  Vec w, ytmp, yerr, k[7];
   long nglobal;
   double t = 0, h = 0, rtol, atol, hmin = 0, hmax = 0, h0 = 0, cfl = 0;
   int fixedstep = 0, mxsteps = 5000, maxnef = 7;
@@ -270,10 +249,18 @@ int main(int argc, char** argv)
   const long N = P.nx * P.ny * P.nz;
   Stepper S;
   S.ctx = ctx;
-  S.T = make_table((int)in.get("order", 4));
+  if (!make_table((int)in.get("order", 4), (int)in.get("etable", -1), S.T)) {
+    fprintf(stderr, "\nERROR: no explicit Butcher table for order = %d / etable = %d (orders 2-5; table ids 0 1 3 6 7 8 12)\n\n",
+            (int)in.get("order", 4), (int)in.get("etable", -1));
+    return 1;
+  }
   S.nglobal = (5 + P.nchem) * N;
   S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
   S.fixedstep = (int)in.get("fixedstep", 0);
+  if (!S.T.embedded && !S.fixedstep) {
+    fprintf(stderr, "\nERROR: this Butcher table has no embedding: it needs fixedstep = 1\n\n");
+    return 1;
+  }
   S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
   S.cfl = in.get("cfl", 0);
   S.mxsteps = (int)in.get("mxsteps", 5000);

@@ -200,3 +200,26 @@ def test_order_overrides_etable_and_unknown_ids_are_refused(pkg):
         d.select_table(0, 13)                             # ARK437L2SA's explicit part: not provided
     with pytest.raises(ValueError):
         d.ERKStep(_OdeOps(), 0.0, None, d.ARKODEParameters(order=0, etable=12))   # no embedding
+
+
+def test_native_driver_tables_equal_the_python_tables(pkg, tmp_path):
+    """host/erk_tables.hpp (native driver) against driver.py: same selection rule, same numbers."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "native_tables_check")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(here, "..", "sundials-manyvector-demo_b200", "host"),
+                           "-o", exe, os.path.join(here, "native_tables_check.cpp")])
+    d = pkg.driver
+    for order, etable in [(2, -1), (3, -1), (4, -1), (5, -1), (4, 8), (0, -1)] + [(0, t) for t in sorted(d.TABLES_BY_ID)]:
+        out = subprocess.run([exe, str(order), str(etable)], capture_output=True, text=True, check=True).stdout.split("\n")
+        A, b, bhat, p, q = d.select_table(order, etable)
+        s = len(b)
+        assert [int(x) for x in out[0].split()] == [s, p, q, 0 if bhat is None else 1]
+        M = np.array([[float(x) for x in out[1 + i].split()] for i in range(s)])
+        for i in range(s):
+            assert list(M[i, :len(A[i])]) == list(A[i]) and not M[i, len(A[i]):].any()
+        assert [float(x) for x in out[1 + s].split()] == list(b)
+        assert [float(x) for x in out[2 + s].split()] == (list(bhat) if bhat is not None else [0.0] * s)
+    for order, etable in [(6, -1), (0, 13), (0, 2)]:
+        assert subprocess.run([exe, str(order), str(etable)], capture_output=True, text=True).stdout.strip() == "none"
