@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/eulerb200.h"
 #include "rhs_kernel.cuh"
+#include "tracer_kernel.cuh"
 
 namespace eb {
 
