@@ -304,9 +304,6 @@ struct eulerb200_ctx {
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
-  bool split = false;            // EULERB200_SPLIT: species in tracer_kernel (tracer_kernel.cuh)
-  int tracer_variant = 0;
-  size_t tracer_smem_set = 0;
   int pair_sync = 2;                                       // EULERB200_PAIR: 0 CTA-wide barriers, 1/2 pairwise row rendezvous (rhs_kernel.cuh)
 };
 
@@ -328,23 +325,6 @@ const KernelVariant kVariants[] = {
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultVariant = 1;
-
-// Split mode (EULERB200_SPLIT=1, off by default until measured on a B200): the species run in
-// tracer_kernel, the fused kernel only produces the five fluid fields.  EULERB200_TRACER_VARIANT
-// selects threads per CTA / resident CTAs per SM of the tracer kernel.
-struct TracerVariant {
-  void (*fn)(const eb::RhsParams);
-  int threads, ctas;
-  const char* name;
-};
-const TracerVariant kTracerVariants[] = {
-    {eb::tracer_kernel<512, 1>, 512, 1, "512x1 (<=128 regs)"},
-    {eb::tracer_kernel<384, 1>, 384, 1, "384x1 (<=168 regs)"},
-    {eb::tracer_kernel<256, 2>, 256, 2, "256x2 (<=128 regs)"},
-    {eb::tracer_kernel<384, 2>, 384, 2, "384x2 (<=80 regs)"},
-    {eb::tracer_kernel<320, 2>, 320, 2, "320x2 (<=96 regs)"},
-};
-const int kNumTracerVariants = (int)(sizeof(kTracerVariants) / sizeof(kTracerVariants[0]));
 
 int fail(eulerb200_ctx* c, int code, const std::string& msg)
 {
@@ -380,7 +360,6 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   }
   for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
   P.slow_mode = 0;
-  P.skip_tracers = 0;
   P.pair_sync = 0;
   P.inv_energy_units = 1.0;
   P.et_rw = nullptr;
@@ -398,10 +377,8 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     if (hi[d] <= lo[d]) return 0;
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
-  const bool split = c->split && P.nchem > 0 && !P.slow_mode;
-  P.skip_tracers = split ? 1 : 0;
   const KernelVariant& V = kVariants[c->variant];
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, split ? 0 : P.nchem, V.threads, c->pair_sync);
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
   P.seg_len = L.seg_len;
   P.pair_sync = L.pair;
   if (L.smem > c->max_smem_set) {
@@ -418,23 +395,6 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
   V.fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
-  if (split) {
-    const TracerVariant& TV = kTracerVariants[c->tracer_variant];
-    const eb::LaunchGeom G = eb::launch_geom(P.lo, P.hi, 0, TV.threads, 0);
-    const size_t smem = sizeof(double) * (size_t)eb::tracer_smem_doubles(G.tx, G.ty);
-    P.seg_len = G.seg_len;
-    P.pair_sync = 0;
-    if (smem > c->tracer_smem_set) {
-      EB_CUDA(c, cudaFuncSetAttribute(TV.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int pct = (int)std::min<size_t>(100, (100 * TV.ctas * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
-      EB_CUDA(c, cudaFuncSetAttribute(TV.fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-      c->tracer_smem_set = smem;
-    }
-    const unsigned npair = (unsigned)((P.nchem + 1) / 2);
-    TV.fn<<<dim3(G.gx * npair, G.gy, G.gz), dim3(G.tx, G.ty, 1), smem, s>>>(P);
-    c->launches++;
-    EB_CUDA(c, cudaGetLastError());
-  }
   return 0;
 }
 
@@ -624,8 +584,6 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
-  if (const char* ev = getenv("EULERB200_SPLIT")) c->split = (atoi(ev) != 0);
-  if (const char* ev = getenv("EULERB200_TRACER_VARIANT")) c->tracer_variant = std::max(0, std::min(kNumTracerVariants - 1, atoi(ev)));
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));

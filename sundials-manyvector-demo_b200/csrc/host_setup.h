@@ -9,7 +9,6 @@
 #include <vector>
 #include "../../include/eulerb200.h"
 #include "rhs_kernel.cuh"
-#include "tracer_kernel.cuh"
 
 namespace eb {
 

@@ -62,7 +62,6 @@ struct RhsParams {
   // and afterwards  chemdot[nchem-1] = etdot,  etdot = 0        (:1059-1068).
   int pair_sync;                      // rows of the tile rendezvous pairwise (see rhs_fused_kernel)
   int slow_mode;
-  int skip_tracers;                   // split mode: the species are left to tracer_kernel (tracer_kernel.cuh)
   double inv_energy_units;
   double* et_rw;            // w[4] again, writable, for the rebuild (slow mode only)
   // sub-box of cells to evaluate: [lo, hi) per axis (the whole box for a single launch;
@@ -190,7 +189,7 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   emit(f2, f[3]);
   emit(4, f[4]);
 
-  if (P.nchem > 0 && !P.skip_tracers) {
+  if (P.nchem > 0) {
     double up[6], um[6];
 #pragma unroll
     for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   EB_DYN_SMEM(double, smem);
   const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
-  const int nv = P.skip_tracers ? 5 : 5 + P.nchem;
+  const int nv = 5 + P.nchem;
   const bool pair = P.pair_sync != 0;
   const bool two_fy = P.pair_sync == 1;
   // the face-only top row of the tile never touches FX / ZLO: those arrays are [NVAR][TR]

@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 
 def build():
     deps = [os.path.join(HERE, f) for f in ("emu_rhs.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "tracer_kernel.cuh", "euler_math.cuh", "host_setup.h")]
+           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "euler_math.cuh", "host_setup.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-ffp-contract=off",
                                "-o", SO, os.path.join(HERE, "emu_rhs.cpp")])
@@ -37,7 +37,7 @@ class Emu:
         self.lib.emu_rhs.restype = C.c_int
 
     def rhs(self, n, nchem, d, gamma, bcs, nbr, rank, w, forcing=None, recv=None, lo=None, hi=None, threads=256,
-            use_aux=1, energy_units=0.0, pair=0, split=0, tracer_threads=384):
+            use_aux=1, energy_units=0.0, pair=0):
         c = self.pkg.Config()
         c.nxl, c.nyl, c.nzl = n
         c.nchem, c.device = nchem, -1
@@ -52,5 +52,5 @@ class Emu:
         bits = C.c_int(0)
         L3 = C.c_long * 3
         ret = self.lib.emu_rhs(C.byref(c), _ptrs(w), _ptrs(out), _ptrs(recv) if recv is not None else None,
-                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair, split, tracer_threads)
+                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair)
         return ret, out, bits.value

@@ -8,7 +8,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int split, int tracer_threads)
+                       int threads, int use_aux, double energy_units, int pair)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -21,7 +21,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   for (int f = 0; f < 6; f++)
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
   for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
-  P.slow_mode = 0; P.skip_tracers = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
+  P.slow_mode = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
   if (energy_units > 0.0) {        // fslow mode: the energy rebuild that aux_kernel does on the device
     P.slow_mode = 1;
     P.inv_energy_units = 1.0 / energy_units;
@@ -44,21 +44,11 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.state_flag = &flag;
   const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};
   for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
-  if (split && (P.nchem == 0 || P.slow_mode)) return -78;
-  P.skip_tracers = split ? 1 : 0;
-  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, split ? 0 : P.nchem, threads, pair);
+  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads, pair);
   P.pair_sync = L.pair;
   if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
   P.seg_len = L.seg_len;
   cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
-  if (split) {       // the species in their own kernel, as launch_box() does on the device
-    const eb::LaunchGeom G = eb::launch_geom(P.lo, P.hi, 0, tracer_threads, 0);
-    P.seg_len = G.seg_len;
-    P.pair_sync = 0;
-    const unsigned npair = (unsigned)((P.nchem + 1) / 2);
-    cuda_emu::launch(eb::tracer_kernel<256, 1>, dim3(G.gx * npair, G.gy, G.gz), dim3(G.tx, G.ty, 1),
-                     sizeof(double) * (size_t)eb::tracer_smem_doubles(G.tx, G.ty), P);
-  }
   *state_bits = flag;
   return flag ? -1 : 0;
 }

@@ -72,48 +72,6 @@ def test_emulated_pairwise_row_rendezvous(emu, oracle_mod, port, n, nchem, bcs, 
                    oracle_mod.random_state((3, 20, 17), 0, seed=1), threads=256, pair=2)[0] == -77
 
 
-@pytest.mark.parametrize("n,nchem,bcs,threads,tthreads", [
-    ((12, 9, 7), 2, [N] * 6, 384, 384),
-    ((12, 9, 7), 3, [R] * 6, 256, 256),                  # odd nchem: the last "pair" is one species
-    ((35, 10, 5), 2, [P, P, R, R, N, N], 128, 64),       # several tiles in x and y, mixed ghost maps
-    ((3, 20, 17), 2, [N] * 6, 256, 256),                 # thin x: more arm cells than threads
-    ((7, 6, 26), 4, [R, R, P, P, N, N], 64, 64),         # several z-segments: ring warm-up per segment
-    ((70, 12, 10), 2, [P] * 6, 128, 128),                # interior tiles reading the aux arrays
-    ((33, 9, 4), 10, [D] * 6, 384, 512),                 # the bench's species count; Dirichlet flips the species
-    ((40, 40, 9), 4, [R] * 6, 384, 384),                 # the production tile shape, 2 x 4 tiles
-    ((70, 24, 8), 4, [P] * 6, 256, 256),                 # interior tiles: the pipelined path (32 x 8 tile)
-    ((70, 38, 7), 3, [N, N, R, R, P, P], 384, 384),      # pipelined path, 32 x 12 tile, odd nchem, z wrap
-    ((66, 40, 5), 2, [R] * 6, 384, 512),                 # pipelined path, 32 x 16 tile
-])
-def test_emulated_split_mode_tracer_kernel(emu, oracle_mod, port, n, nchem, bcs, threads, tthreads):
-    """EULERB200_SPLIT path: the fused kernel with skip_tracers plus tracer_kernel.cuh (species
-    pairs, z-ring in registers, double-buffered shared plane copy, one barrier per plane).
-    Against the oracle to 1e-12, and against the fused kernel: the fluid fields bit for bit,
-    the species to a few ulp (ghost cells take c from a differently-ordered |m|^2 sum)."""
-    w = oracle_mod.random_state(n, nchem, seed=sum(n))
-    d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
-    forcing = [0, 0, -0.1, 0, 0]
-    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
-    ret0, fused, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads)
-    assert ret0 == 0 and ret_ref == 0
-    dirichlet = D in bcs                 # non-finite boundary cells, as in the reference (DESIGN.md section 5)
-    for use_aux in (1, 0):
-        ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads,
-                                 use_aux=use_aux, split=1, tracer_threads=tthreads)
-        assert ret == 0 and bits == 0
-        if not dirichlet:
-            assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
-        if use_aux:
-            for f in range(5):
-                assert np.array_equal(got[f], fused[f], equal_nan=True)
-        fin = np.isfinite(fused[5])
-        assert np.array_equal(fin, np.isfinite(got[5]))
-        scale = np.abs(fused[5][fin]).max()
-        assert np.abs(got[5][fin] - fused[5][fin]).max() <= 1e-13 * scale
-    # the split path does not apply without species
-    assert emu.rhs(n, 0, d, 1.4, bcs, nbr_single(bcs), 0, oracle_mod.random_state(n, 0, seed=1), split=1)[0] == -78
-
-
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)
@@ -123,8 +81,7 @@ def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     assert ret == -1 and bits == mask == 6
 
 
-@pytest.mark.parametrize("split", [0, 1])
-def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle_mod, port, split):
+def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle_mod, port):
     """The N>1 kernel path without a GPU: split a periodic/reflecting box over 2 ranks the way
     SetupDecomp does, hand each rank the neighbour's packed layers as its halo buffers
     (wire layout of euler3D.hpp:648), evaluate interior and boundary shells as separate
@@ -157,8 +114,7 @@ def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle
         hi = [nl[a] - (3 if b["nbr"][2 * a + 1] not in (NO, rank) else 0) for a in range(3)]
         boxes = [(lo, hi), ([0, lo[1], lo[2]], [lo[0], hi[1], hi[2]]), ([hi[0], lo[1], lo[2]], [nl[0], hi[1], hi[2]])]
         for blo, bhi in boxes:
-            ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi,
-                                      split=split, tracer_threads=128)
+            ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi)
             assert ret == 0
             for o, p_ in zip(out, part):
                 m = ~np.isnan(p_)

@@ -17,17 +17,13 @@ ap.add_argument("--nchem", type=int, nargs="+", default=[10, 0])
 ap.add_argument("--variants", type=int, nargs="+", default=[0, 1, 2, 3])
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--pair", type=int, nargs="+", default=[2], help="EULERB200_PAIR values to time")
-ap.add_argument("--split", type=int, nargs="+", default=[-1],
-                help="EULERB200_TRACER_VARIANT values to time in split mode (-1: fused kernel)")
 args = ap.parse_args()
 if os.environ.get("EB_TUNE_BUILD"): build()
 pkg = load_package()
 for nchem in args.nchem:
-    for v, pair, tv in [(v, q, tv) for v in args.variants for q in args.pair for tv in args.split]:
+    for v, pair in [(v, q) for v in args.variants for q in args.pair]:
         os.environ["EULERB200_VARIANT"] = str(v)
         os.environ["EULERB200_PAIR"] = str(pair)
-        os.environ["EULERB200_SPLIT"] = "0" if tv < 0 or nchem == 0 else "1"
-        os.environ["EULERB200_TRACER_VARIANT"] = str(max(tv, 0))
         u = pkg.EulerData(nchem=nchem)
         u.nx, u.ny, u.nz = args.n
         u.xlbc = u.xrbc = u.ylbc = u.yrbc = u.zlbc = u.zrbc = pkg.BC_REFLECTING
@@ -46,8 +42,8 @@ for nchem in args.nchem:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         cells = u.nx * u.ny * u.nz
-        print("n=%s nchem=%2d variant=%d pair=%d split=%2d  %8.3f ms  %6.3f Gcell/s  checksum=%.12e %.12e"
-              % (args.n, nchem, v, pair, tv, ms, cells / ms / 1e6, float(wdot.sub[0].double().abs().sum()),
+        print("n=%s nchem=%2d variant=%d pair=%d  %8.3f ms  %6.3f Gcell/s  checksum=%.12e %.12e"
+              % (args.n, nchem, v, pair, ms, cells / ms / 1e6, float(wdot.sub[0].double().abs().sum()),
                  float(wdot.sub[-1].double().abs().sum())), flush=True)
         u.FreeData()
         del w, wdot
