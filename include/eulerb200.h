@@ -112,6 +112,15 @@ int eulerb200_rhs_async(eulerb200_ctx* ctx, double t, const double* const* w, do
                         void* stream);
 int eulerb200_state_flag(eulerb200_ctx* ctx, void* stream, int32_t* bits);
 
+/* The external_forces hook in full generality (euler3D.hpp:1454, called at utilities.cpp:65, where
+ * it ASSIGNS G into wdot before the flux divergence is subtracted).  Constant-per-field forcing
+ * lives in the config.  For a hook that varies in space or time, switch this on and run the hook
+ * on wdot yourself before every eulerb200_rhs* call, exactly as the reference's fEuler does
+ * (N_VConst(0, wdot); external_forces(t, wdot, udata)): the kernel then computes
+ * wdot = wdot - div F(w) cell by cell, config.forcing is ignored, and eulerb200_rhs_host uploads
+ * wdot along with w. */
+int eulerb200_set_forcing_in_wdot(eulerb200_ctx* ctx, int32_t on);
+
 /* fslow / fexpl of the multirate and IMEX drivers, fused (multirate_chem_hydro_main.cpp:
  * 996-1083, imex_chem_hydro_main.cpp:910-1000): rebuild the total energy from the gas energy
  * carried as the last chemistry species, et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho) -- written

@@ -61,6 +61,16 @@ def build_dropin():
     return True
 
 
+def build_dropin_emu():
+    """The same link check against the CPU emulation of the kernel source (tests/emu/emu_abi.cpp)
+    instead of libeulerb200.so, so that the CPU test tier can run the drop-in's host logic next to
+    the unmodified reference fEuler.  Returns the binary's path, or None without the reference."""
+    exe = os.path.join(REF_DIR, "dropin_check_emu_nvar7")
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "dropin_emu", "REFERENCE=" + REFERENCE_ROOT])
+    return exe if os.path.exists(exe) else None
+
+
 def have_ref(nvar=5):
     return os.path.exists(os.path.join(REF_DIR, "libref_nvar%d.so" % nvar))
 

@@ -14,6 +14,8 @@
  * ------------------------------------------------------------------------- */
 #include <euler3D.hpp>
 #include <cstdint>
+#include <cmath>
+#include <cstdlib>
 
 int ref_fEuler(realtype t, N_Vector w, N_Vector wdot, void* user_data);
 int ref_stability(N_Vector w, realtype t, realtype* dt_stab, void* user_data);
@@ -22,9 +24,22 @@ void shim_set_world(int nprocs);
 void shim_set_rank(int rank);
 
 static double g_gmy = 0.0;
+static int g_varying = 0;       // EB_DROPIN_VARYING=1: a hook that depends on position and time
 int external_forces(const realtype& t, N_Vector G, const EulerData& udata)
 {
-  (void)t;
+  if (g_varying) {
+    const long N = udata.nxl * udata.nyl * udata.nzl;
+    const int fields[3] = {1, 2, 4};
+    for (int q = 0; q < 3; q++) {
+      realtype* g = N_VGetSubvectorArrayPointer_MPIManyVector(G, fields[q]);
+      for (long i = 0; i < N; i++) g[i] = 0.05 * std::sin(0.1 * i + fields[q]) + 0.01 * t;
+    }
+    if (udata.nchem > 0) {
+      realtype* g = N_VGetSubvectorArrayPointer_MPIManyVector(G, 5);
+      for (long i = 0; i < N * udata.nchem; i++) g[i] = 1e-3 * std::cos(0.3 * i) * (1.0 + t);
+    }
+    return 0;
+  }
   if (g_gmy == 0.0) return 0;
   realtype* g = N_VGetSubvectorArrayPointer_MPIManyVector(G, 2);
   for (long i = 0; i < udata.nxl * udata.nyl * udata.nzl; i++) g[i] = g_gmy;
@@ -66,8 +81,9 @@ static int run_case(long nx, long ny, long nz, const int bc[6], double gmy)
     w.sub[4]->data[i] = u.eos_inv(rho, rho * vx, rho * vy, rho * vz, p);
     for (int v = 0; v < u.nchem; v++) w.sub[5]->data[i * u.nchem + v] = urand();
   }
-  const int r1 = ref_fEuler(0.0, w.v, a.v, (void*)&u);
-  const int r2 = fEuler(0.0, w.v, b.v, (void*)&u);
+  const double tcall = g_varying ? 0.3 : 0.0;
+  const int r1 = ref_fEuler(tcall, w.v, a.v, (void*)&u);
+  const int r2 = fEuler(tcall, w.v, b.v, (void*)&u);
   double worst = 0.0;
   double mom = 0.0;
   for (int f = 1; f <= 3; f++) for (long i = 0; i < N; i++) mom = std::max(mom, std::fabs(a.sub[f]->data[i]));
@@ -85,6 +101,7 @@ static int run_case(long nx, long ny, long nz, const int bc[6], double gmy)
   const int s2 = stability(w.v, 0.0, &dt2, (void*)&u);
   const double dterr = std::fabs(dt1 - dt2) / dt1;
   const bool ok = r1 == 0 && r2 == 0 && s1 == 0 && s2 == 0 && worst <= 1e-12 && dterr <= 1e-14;
+  if (g_varying) printf("[position- and time-dependent external_forces hook, run before every evaluation] ");
   printf("NVAR=%d grid %ldx%ldx%ld bc [%d %d %d %d %d %d] Gmy=%g : ret %d/%d  max normwise err %.3e  dt_stab rel err %.1e  %s\n",
          NVAR, nx, ny, nz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5], gmy, r1, r2, worst, dterr, ok ? "ok" : "MISMATCH");
   eulerb200_dropin_release((void*)&u);
@@ -95,6 +112,7 @@ int main()
 {
   shim_set_world(1); shim_set_rank(0);
   int bad = 0;
+  g_varying = (getenv("EB_DROPIN_VARYING") != NULL);
   const int per[6] = {0, 0, 0, 0, 0, 0}, neu[6] = {1, 1, 1, 1, 1, 1}, rt[6] = {0, 0, 3, 3, 1, 1}, refl[6] = {3, 3, 3, 3, 3, 3};
   bad += run_case(24, 20, 16, per, 0.0);
   bad += run_case(24, 20, 16, neu, 0.0);

@@ -12,7 +12,8 @@ reference (``/root/reference/src``)    here
 ``N_VMake_MPIManyVector`` 5+1 subvecs  :class:`ManyVector` (5 fluid + 1 chem sub-vectors)
 ``fEuler`` utilities.cpp:17            :func:`fEuler`
 ``stability`` utilities.cpp:483        :func:`stability`
-``external_forces`` hook               ``EulerData.forcing`` (constant per fluid field)
+``external_forces`` hook               ``EulerData.forcing`` (constant per fluid field), or
+                                       ``fEuler(..., external_forces=hook)`` for any hook
 =====================================  ==================================================
 
 PyTorch is used for device memory, streams and ``torch.distributed`` only.  There is no
@@ -79,6 +80,7 @@ ABI = {
     "eulerb200_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),
+    "eulerb200_set_forcing_in_wdot": (C.c_int, [C.c_void_p, C.c_int32]),
     "eulerb200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }
 
@@ -337,15 +339,29 @@ class EulerData:
         return load_library().eulerb200_last_error(self._ctx).decode()
 
 
-def fEuler(t, w, wdot, user_data, sync=True):
+def fEuler(t, w, wdot, user_data, sync=True, external_forces=None):
     """``int fEuler(realtype t, N_Vector w, N_Vector wdot, void* user_data)``
     (utilities.cpp:17-253).  Returns 0, or -1 on an illegal state / failure like the
     reference.  Device vectors run on the current CUDA stream; host vectors go through
-    the staged host path.  ``sync=False`` skips the legal-state read-back (no host sync)."""
+    the staged host path.  ``sync=False`` skips the legal-state read-back (no host sync).
+
+    ``external_forces(t, G, user_data) -> int`` is the reference's link-time hook
+    (euler3D.hpp:1454) for forcing that is not a per-field constant: as at utilities.cpp:28,65
+    ``wdot`` is zeroed, the hook ASSIGNS G into it, and the kernel subtracts the flux
+    divergence from what it finds there (``user_data.forcing`` is then ignored)."""
     lib = load_library()
     u = user_data
     if u._ctx is None:
         raise EulerB200Error("EulerData.SetupDecomp() has not been called")
+    if bool(external_forces) != getattr(u, "_forcing_in_wdot", False):
+        if lib.eulerb200_set_forcing_in_wdot(u._ctx, 1 if external_forces else 0) != 0:
+            return -1
+        u._forcing_in_wdot = bool(external_forces)
+    if external_forces:
+        for sub in wdot.sub:
+            sub.zero_()
+        if external_forces(float(t), wdot, u) != 0:
+            return -1
     if w.is_cuda:
         fn = lib.eulerb200_rhs if sync else lib.eulerb200_rhs_async
         return fn(u._ctx, float(t), w.pointers(), wdot.pointers(), u._stream())

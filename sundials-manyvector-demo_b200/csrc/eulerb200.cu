@@ -300,7 +300,8 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set = 0, carveout_for = (size_t)-1;
+  size_t max_smem_set[2] = {0, 0}, carveout_for[2] = {(size_t)-1, (size_t)-1};   // [plain, forcing-in-wdot kernel]
+  bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
@@ -313,15 +314,15 @@ namespace {
 // register budget (65536 / (threads * CTAs)).  EULERB200_VARIANT selects one by index for
 // tuning runs; the default is the fastest measured on B200 (profiles/).
 struct KernelVariant {
-  void (*fn)(const eb::RhsParams);
+  void (*fn[2])(const eb::RhsParams);     // [0] constant forcing, [1] G taken from wdot (GW instantiation)
   int threads;
   const char* name;
 };
 const KernelVariant kVariants[] = {
-    {eb::rhs_fused_kernel<256, 1>, 256, "256x1 (<=255 regs)"},
-    {eb::rhs_fused_kernel<384, 1>, 384, "384x1 (<=168 regs)"},
-    {eb::rhs_fused_kernel<512, 1>, 512, "512x1 (<=128 regs)"},
-    {eb::rhs_fused_kernel<256, 2>, 256, "256x2 (<=128 regs)"},
+    {{eb::rhs_fused_kernel<256, 1>, eb::rhs_fused_kernel<256, 1, true>}, 256, "256x1 (<=255 regs)"},
+    {{eb::rhs_fused_kernel<384, 1>, eb::rhs_fused_kernel<384, 1, true>}, 384, "384x1 (<=168 regs)"},
+    {{eb::rhs_fused_kernel<512, 1>, eb::rhs_fused_kernel<512, 1, true>}, 512, "512x1 (<=128 regs)"},
+    {{eb::rhs_fused_kernel<256, 2>, eb::rhs_fused_kernel<256, 2, true>}, 256, "256x2 (<=128 regs)"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultVariant = 1;
@@ -378,21 +379,23 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
   const KernelVariant& V = kVariants[c->variant];
+  const int gw = c->forcing_in_wdot ? 1 : 0;
+  void (*const fn)(const eb::RhsParams) = V.fn[gw];
   const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
   P.seg_len = L.seg_len;
   P.pair_sync = L.pair;
-  if (L.smem > c->max_smem_set) {
-    EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    c->max_smem_set = L.smem;
+  if (L.smem > c->max_smem_set[gw]) {
+    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    c->max_smem_set[gw] = L.smem;
   }
-  if (L.smem != c->carveout_for) {
+  if (L.smem != c->carveout_for[gw]) {
     // the stencil loads live in L1: ask for the smallest shared-memory carve-out that holds one CTA
     // (+1 KB the system reserves per CTA) and leave the rest of the 256 KB to L1
     const int pct = (int)std::min<size_t>(100, (100 * (L.smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
-    EB_CUDA(c, cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    c->carveout_for = L.smem;
+    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    c->carveout_for[gw] = L.smem;
   }
-  V.fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
+  fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
@@ -910,8 +913,11 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
   { int rc_ = ensure_staging(c); if (rc_) return rc_; }
   if (c->any_remote) {
     // with remote neighbours the halo exchange needs the whole state: no slab pipeline
-    for (int f = 0; f < nsub; f++)
+    for (int f = 0; f < nsub; f++) {
       EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f], wh[f], sizeof(double) * N * (f < 5 ? 1 : g.nchem), cudaMemcpyHostToDevice, c->s_cmp));
+      if (c->forcing_in_wdot)      // the hook's G travels with the state
+        EB_CUDA(c, cudaMemcpyAsync(c->stage_wdot[f], wdh[f], sizeof(double) * N * (f < 5 ? 1 : g.nchem), cudaMemcpyHostToDevice, c->s_cmp));
+    }
     int rc = eulerb200_rhs_async(c, t, c->stage_w, c->stage_wdot, c->s_cmp);
     if (rc) return rc;
     for (int f = 0; f < nsub; f++)
@@ -930,6 +936,9 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
         const long m = (f < 5 ? 1 : g.nchem);
         EB_CUDA(c, cudaMemcpyAsync(c->stage_w[f] + zb[s] * plane * m, wh[f] + zb[s] * plane * m,
                                    sizeof(double) * (zb[s + 1] - zb[s]) * plane * m, cudaMemcpyHostToDevice, c->s_h2d));
+        if (c->forcing_in_wdot)    // the hook's G travels with the state
+          EB_CUDA(c, cudaMemcpyAsync(c->stage_wdot[f] + zb[s] * plane * m, wdh[f] + zb[s] * plane * m,
+                                     sizeof(double) * (zb[s + 1] - zb[s]) * plane * m, cudaMemcpyHostToDevice, c->s_h2d));
       }
       EB_CUDA(c, cudaEventRecord(c->ev_up[s], c->s_h2d));
     }
@@ -1077,6 +1086,13 @@ int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes)
 }
 
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
+
+int eulerb200_set_forcing_in_wdot(eulerb200_ctx* c, int32_t on)
+{
+  if (!c) return -1;
+  c->forcing_in_wdot = (on != 0);
+  return 0;
+}
 
 int eulerb200_fp64_peak(double* tflops)
 {

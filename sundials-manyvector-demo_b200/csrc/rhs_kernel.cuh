@@ -298,7 +298,9 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // array does not fit).
 // Rows then drift apart by up to a phase per hop instead of all waiting for the slowest twice per
 // plane, so their load bursts and FP64 stretches overlap.
-template <int MAXT, int MINB>
+// GW: the forcing is not the per-field constant of the config; the caller has run the
+// external_forces hook into wdot (utilities.cpp:65) and every store is wdot = wdot - div.
+template <int MAXT, int MINB, bool GW = false>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
@@ -362,7 +364,19 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)
                                         + (zup - ZLO[v * TR]) * P.rdz;
                       ZLO[v * TR] = zup;
-                      if (!P.slow_mode) {
+                      if (GW) {
+                        // the caller ran external_forces itself: wdot already holds G (utilities.cpp:65)
+                        double* dst = (v < 5) ? P.wdot[v] + cell : P.wdot[5] + cell * P.nchem + (v - 5);
+                        const double G = *dst;
+                        if (!P.slow_mode) {
+                          st_out(dst, G - div);
+                        } else if (v == 4) {
+                          st_out(P.wdot[5] + cell * P.nchem + (P.nchem - 1), G - div);
+                          st_out(dst, 0.0);
+                        } else if (v < 4 + P.nchem) {
+                          st_out(dst, G - div);
+                        }
+                      } else if (!P.slow_mode) {
                         if (v < 5) st_out(P.wdot[v] + cell, P.forcing[v] - div);
                         else st_out(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
                       } else if (v == 4) {          // etdot goes to the gas-energy species

@@ -18,8 +18,11 @@
 // Forcing: the reference calls the link-time hook external_forces(t, wdot, udata) inside
 // fEuler (utilities.cpp:65), which ASSIGNS G into wdot.  Every shipped problem assigns a
 // constant per field (zero, or Gmy = -0.1 for Rayleigh-Taylor), so the hook is evaluated
-// once on a small host probe vector when the context is created and its constants are
-// handed to the kernel; a hook that is not constant in space is rejected loudly.
+// once on a host probe vector when the context is created (at t0 and at a later time) and,
+// if it is such a constant, its values are handed to the kernel.  Any other hook is run on
+// wdot before every evaluation exactly as the reference does (utilities.cpp:28,65) and the
+// kernel subtracts the flux divergence from what it finds there
+// (eulerb200_set_forcing_in_wdot).
 //
 // Multi-rank: the NCCL id (MPI_Bcast) and the CUDA-IPC mailbox handles of the peer-store halo
 // transport (MPI_Allgather) travel once, at context creation, over the reference's own
@@ -32,15 +35,16 @@
 
 namespace {
 
-struct Binding { eulerb200_ctx* ctx; };
+struct Binding { eulerb200_ctx* ctx; bool hook_per_call; };
 std::map<const EulerData*, Binding>& bindings()
 {
   static std::map<const EulerData*, Binding> m;
   return m;
 }
 
-// Evaluate the external_forces hook on a probe the size of the local block and reduce it
-// to one constant per fluid field.
+// Evaluate the external_forces hook on a probe the size of the local block, at t0 and at a
+// later time, and reduce it to one constant per fluid field.  Returns 0 if it is such a
+// constant (and zero for the species), 1 if it is not, -1 if the hook fails.
 int probe_forcing(EulerData* udata, double forcing[5])
 {
   const long N = udata->nxl * udata->nyl * udata->nzl;
@@ -49,24 +53,25 @@ int probe_forcing(EulerData* udata, double forcing[5])
   for (int f = 0; f < 5; f++) sub[f] = N_VNew_Serial(N, udata->ctx);
   if (udata->nchem > 0) sub[5] = N_VNew_Serial(N * udata->nchem, udata->ctx);
   N_Vector G = N_VMake_MPIManyVector(udata->comm, nsub, sub, udata->ctx);
-  N_VConst(ZERO, G);
-  int ret = external_forces(udata->t0, G, *udata);
-  for (int f = 0; f < 5 && ret == 0; f++) {
-    const realtype* g = N_VGetArrayPointer(sub[f]);
-    forcing[f] = g[0];
-    for (long i = 1; i < N; i++)
-      if (g[i] != g[0]) { ret = -1; break; }
-  }
-  if (ret == 0 && udata->nchem > 0) {
-    const realtype* g = N_VGetArrayPointer(sub[5]);
-    for (long i = 0; i < N * udata->nchem; i++)
-      if (g[i] != ZERO) { ret = -1; break; }
+  int ret = 0;
+  const double times[2] = {udata->t0, udata->t0 + 0.37 * (udata->tf - udata->t0) + 1.0};
+  for (int pass = 0; pass < 2 && ret == 0; pass++) {
+    N_VConst(ZERO, G);
+    if (external_forces(times[pass], G, *udata) != 0) { ret = -1; break; }
+    for (int f = 0; f < 5 && ret == 0; f++) {
+      const realtype* g = N_VGetArrayPointer(sub[f]);
+      if (pass == 0) forcing[f] = g[0];
+      for (long i = 0; i < N; i++)
+        if (g[i] != forcing[f]) { ret = 1; break; }
+    }
+    if (ret == 0 && udata->nchem > 0) {
+      const realtype* g = N_VGetArrayPointer(sub[5]);
+      for (long i = 0; i < N * udata->nchem; i++)
+        if (g[i] != ZERO) { ret = 1; break; }
+    }
   }
   N_VDestroy(G);
   for (int f = 0; f < nsub; f++) N_VDestroy(sub[f]);
-  if (ret != 0)
-    cerr << "\neulerb200: external_forces is not a per-field constant; the B200 fluid RHS "
-            "supports constant forcing only\n\n";
   return ret;
 }
 
@@ -88,7 +93,9 @@ eulerb200_ctx* context_for(EulerData* udata)
   }
   c.rank = udata->myid;
   c.nranks = udata->nprocs;
-  if (probe_forcing(udata, c.forcing) != 0) return NULL;
+  const int probe = probe_forcing(udata, c.forcing);
+  if (probe < 0) return NULL;
+  if (probe == 1) for (int f = 0; f < 5; f++) c.forcing[f] = 0.0;   // the hook runs before every evaluation
   eulerb200_ctx* ctx = NULL;
   if (eulerb200_create(&c, &ctx) != 0) {
     cerr << "\neulerb200_create failed: " << eulerb200_last_error(NULL) << "\n\n";
@@ -117,7 +124,9 @@ eulerb200_ctx* context_for(EulerData* udata)
       return NULL;
     }
   }
+  if (probe == 1 && eulerb200_set_forcing_in_wdot(ctx, 1) != 0) return NULL;
   bindings()[udata].ctx = ctx;
+  bindings()[udata].hook_per_call = (probe == 1);
   return ctx;
 }
 
@@ -154,6 +163,11 @@ int fEuler(realtype t, N_Vector w, N_Vector wdot, void* user_data)
 
   eulerb200_ctx* ctx = context_for(udata);
   if (ctx == NULL) return -1;
+  if (bindings()[udata].hook_per_call) {       // utilities.cpp:28,65
+    N_VConst(ZERO, wdot);
+    retval = external_forces(t, wdot, *udata);
+    if (check_flag(&retval, "external_forces (fEuler)", 1)) return -1;
+  }
   retval = eulerb200_rhs_any(ctx, t, wp, wdp, NULL);
   if (retval != 0) {
     cerr << "\n" << eulerb200_last_error(ctx) << "\n\n";

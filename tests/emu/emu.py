@@ -37,7 +37,7 @@ class Emu:
         self.lib.emu_rhs.restype = C.c_int
 
     def rhs(self, n, nchem, d, gamma, bcs, nbr, rank, w, forcing=None, recv=None, lo=None, hi=None, threads=256,
-            use_aux=1, energy_units=0.0, pair=0):
+            use_aux=1, energy_units=0.0, pair=0, g_in_wdot=None):
         c = self.pkg.Config()
         c.nxl, c.nyl, c.nzl = n
         c.nchem, c.device = nchem, -1
@@ -49,8 +49,10 @@ class Emu:
             c.forcing[f] = forcing[f] if forcing is not None else 0.0
         N = n[0] * n[1] * n[2]
         out = [np.full(N, np.nan) for _ in range(5)] + [np.full(N * nchem, np.nan) if nchem else None]
+        if g_in_wdot is not None:         # the external_forces hook has assigned G into wdot
+            out = [None if g is None else np.array(g, dtype=np.float64, copy=True) for g in g_in_wdot]
         bits = C.c_int(0)
         L3 = C.c_long * 3
         ret = self.lib.emu_rhs(C.byref(c), _ptrs(w), _ptrs(out), _ptrs(recv) if recv is not None else None,
-                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair)
+                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair, 0 if g_in_wdot is None else 1)
         return ret, out, bits.value

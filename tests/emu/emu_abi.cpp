@@ -1,0 +1,62 @@
+// ---------------------------------------------------------------------------
+// emu_abi.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE, never shipped or loaded by the product.
+//
+// The handful of C-ABI entry points (include/eulerb200.h) that the drop-in fEuler / stability of
+// sundials-manyvector-demo_b200/host/feuler_dropin.cpp calls, implemented on top of the CPU
+// emulation of the kernel SOURCE (emu_rhs.cpp), single rank.  It exists so that the "not gpu"
+// tier can link the drop-in against the reference's own EulerData and run it next to the
+// unmodified reference fEuler (oracle/dropin_check.cpp) without a GPU: that checks the host
+// logic of the drop-in (probe of the external_forces hook, per-call hook, pointer plumbing,
+// error paths), nothing about the device library.
+// ---------------------------------------------------------------------------
+#include <cmath>
+#include <string>
+#include "../../include/eulerb200.h"
+
+extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
+                       const double* const* recv, int* state_bits, const long* lo, const long* hi,
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot);
+
+struct eulerb200_ctx { eulerb200_config cfg; bool gw; std::string err; };
+static std::string g_err;
+
+extern "C" {
+int eulerb200_version(void) { return EULERB200_VERSION; }
+int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
+{
+  if (!cfg || !out || cfg->nranks != 1) { g_err = "emu_abi: single rank only"; return -1; }
+  *out = new eulerb200_ctx{*cfg, false, ""};
+  return 0;
+}
+int eulerb200_destroy(eulerb200_ctx* c) { delete c; return 0; }
+const char* eulerb200_last_error(const eulerb200_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+int eulerb200_set_forcing_in_wdot(eulerb200_ctx* c, int32_t on) { if (!c) return -1; c->gw = on != 0; return 0; }
+int eulerb200_rhs_any(eulerb200_ctx* c, double, const double* const* w, double* const* wdot, void*)
+{
+  int bits = 0;
+  const int rc = emu_rhs(&c->cfg, w, wdot, nullptr, &bits, nullptr, nullptr, 128, 1, 0.0, 0, c->gw ? 1 : 0);
+  if (rc) c->err = "STATE_ERROR: legal_state (fEuler) failed with flag = " + std::to_string(bits);
+  return rc;
+}
+int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void*)
+{
+  // utilities.cpp:505-520, same expression as wavespeed_kernel
+  const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
+  const double g = c->cfg.gamma;
+  double alpha = 0.0;
+  for (long i = 0; i < N; i++) {
+    const double r = w[0][i], a = w[1][i], b = w[2][i], d = w[3][i];
+    const double p = (g - 1.0) * (w[4][i] - (a * a + b * b + d * d) * 0.5 / r);
+    const double s = g * p / r;
+    const double x = std::fabs(std::fabs(a / r) + (s <= 0.0 ? 0.0 : std::sqrt(s)));
+    alpha = alpha < x ? x : alpha;
+  }
+  *dt_stab = cfl * std::fmin(std::fmin(c->cfg.dx, c->cfg.dy), c->cfg.dz) / alpha;
+  return 0;
+}
+// multi-rank entry points the drop-in references but never reaches with one rank
+int eulerb200_comm_unique_id(void*) { return -1; }
+int eulerb200_comm_attach(eulerb200_ctx*, const void*) { return -1; }
+int eulerb200_p2p_export(eulerb200_ctx*, void*) { return -1; }
+int eulerb200_p2p_attach(eulerb200_ctx*, const void*) { return -1; }
+}

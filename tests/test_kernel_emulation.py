@@ -72,6 +72,35 @@ def test_emulated_pairwise_row_rendezvous(emu, oracle_mod, port, n, nchem, bcs, 
                    oracle_mod.random_state((3, 20, 17), 0, seed=1), threads=256, pair=2)[0] == -77
 
 
+@pytest.mark.parametrize("n,nchem,bcs,threads", [
+    ((12, 9, 7), 2, [N] * 6, 384),
+    ((35, 10, 5), 3, [P, P, R, R, N, N], 128),
+    ((70, 12, 10), 0, [P] * 6, 128),
+])
+def test_emulated_forcing_taken_from_wdot(emu, oracle_mod, port, n, nchem, bcs, threads):
+    """eulerb200_set_forcing_in_wdot (the GW kernel instantiation): the caller has run an arbitrary
+    external_forces hook into wdot (utilities.cpp:28,65) and the kernel computes wdot = wdot - div F.
+    fEuler is affine in G and the reference rounds G - div once, so the expected result is exactly
+    G + (oracle with zero forcing)."""
+    w = oracle_mod.random_state(n, nchem, seed=3 + sum(n))
+    d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+    rng = np.random.default_rng(5)
+    N_ = n[0] * n[1] * n[2]
+    G = [rng.normal(size=N_) for _ in range(5)] + [rng.normal(size=N_ * nchem) if nchem else None]
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+    want = [None if r is None else g + r for g, r in zip(G, ref)]
+    ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=[9, 9, 9, 9, 9], threads=threads,
+                             g_in_wdot=G)
+    assert ret == 0 and ret_ref == 0 and bits == 0
+    floor = rounding_floor(w, 1.4, d)
+    assert max(normwise_errors(got, want, floor)) <= 1e-12
+    # bit for bit the plain kernel's divergence: got - G == plain(zero forcing) up to the one rounding of G - div
+    ret0, plain, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads)
+    for g, a, b in zip(G, got, plain):
+        if g is not None:
+            assert np.array_equal(a, g + b)
+
+
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)
@@ -147,3 +176,7 @@ def test_emulated_slow_mode_matches_reference_sequence(emu, oracle_mod, port):
     floor = rounding_floor(ref_w, 1.4, d)
     floor[4] = 0.0
     assert max(normwise_errors(got, ref, floor)) <= 1e-12
+    # the forcing-from-wdot instantiation takes the same redirected stores: with G = 0 in wdot, same bits
+    zeros = [np.zeros_like(x) for x in got]
+    ret, got_gw, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, energy_units=eu, g_in_wdot=zeros)
+    assert ret == 0 and all(np.array_equal(a, b) for a, b in zip(got, got_gw))
