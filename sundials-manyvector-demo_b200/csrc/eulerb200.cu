@@ -300,8 +300,9 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set[2] = {0, 0}, carveout_for[2] = {(size_t)-1, (size_t)-1};   // [plain, forcing-in-wdot kernel]
+  size_t max_smem_set[3] = {0, 0, 0}, carveout_for[3] = {(size_t)-1, (size_t)-1, (size_t)-1};   // per kernel instantiation
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
+  int force_kernel = 0;          // EULERB200_KERNEL=1: allow the AG instantiation for boundary-heavy launches
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
@@ -314,15 +315,19 @@ namespace {
 // register budget (65536 / (threads * CTAs)).  EULERB200_VARIANT selects one by index for
 // tuning runs; the default is the fastest measured on B200 (profiles/).
 struct KernelVariant {
-  void (*fn[2])(const eb::RhsParams);     // [0] constant forcing, [1] G taken from wdot (GW instantiation)
+  // [0] the measured default; [1] AG: boundary tiles read the per-cell arrays where valid (for
+  // launches that are mostly boundary tiles; opt-in with EULERB200_KERNEL=1 until it has been
+  // timed on a B200); [2] GW: G taken from wdot (hook-assigned forcing)
+  void (*fn[3])(const eb::RhsParams);
   int threads;
   const char* name;
 };
+#define EB_KERNELS(T, B) {eb::rhs_fused_kernel<T, B>, eb::rhs_fused_kernel<T, B, false, true>, eb::rhs_fused_kernel<T, B, true, false>}
 const KernelVariant kVariants[] = {
-    {{eb::rhs_fused_kernel<256, 1>, eb::rhs_fused_kernel<256, 1, true>}, 256, "256x1 (<=255 regs)"},
-    {{eb::rhs_fused_kernel<384, 1>, eb::rhs_fused_kernel<384, 1, true>}, 384, "384x1 (<=168 regs)"},
-    {{eb::rhs_fused_kernel<512, 1>, eb::rhs_fused_kernel<512, 1, true>}, 512, "512x1 (<=128 regs)"},
-    {{eb::rhs_fused_kernel<256, 2>, eb::rhs_fused_kernel<256, 2, true>}, 256, "256x2 (<=128 regs)"},
+    {EB_KERNELS(256, 1), 256, "256x1 (<=255 regs)"},
+    {EB_KERNELS(384, 1), 384, "384x1 (<=168 regs)"},
+    {EB_KERNELS(512, 1), 512, "512x1 (<=128 regs)"},
+    {EB_KERNELS(256, 2), 256, "256x2 (<=128 regs)"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultVariant = 1;
@@ -379,9 +384,14 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
   const KernelVariant& V = kVariants[c->variant];
-  const int gw = c->forcing_in_wdot ? 1 : 0;
-  void (*const fn)(const eb::RhsParams) = V.fn[gw];
   const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
+  // which instantiation: hook-assigned forcing -> [2]; with EULERB200_KERNEL=1 a launch in which a
+  // quarter or more of the tiles touch a boundary (thin or small grids, the boundary shells of a
+  // decomposed run) -> [1]; else the default [0]
+  int gw = 0;
+  if (c->forcing_in_wdot) gw = 2;
+  else if (c->force_kernel == 1 && c->use_aux && eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) gw = 1;
+  void (*const fn)(const eb::RhsParams) = V.fn[gw];
   P.seg_len = L.seg_len;
   P.pair_sync = L.pair;
   if (L.smem > c->max_smem_set[gw]) {
@@ -587,6 +597,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
+  if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) == 1) ? 1 : 0;
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));

@@ -173,4 +173,21 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   return L;
 }
 
+// Fraction of the tiles of a launch whose x- or y-stencils reach beyond the owned range (the
+// CTA-uniform gen_x / gen_y test of rhs_fused_kernel).
+inline double boundary_tile_fraction(const long lo[3], const long hi[3], long nx, long ny, const LaunchGeom& L)
+{
+  (void)hi;
+  long okx = 0, oky = 0;
+  for (unsigned b = 0; b < L.gx; b++) {
+    const long t0 = lo[0] + (long)b * (L.tx - 1);
+    if (!(t0 - 3 < 0 || t0 + L.tx - 1 + 2 >= nx)) okx++;
+  }
+  for (unsigned b = 0; b < L.gy; b++) {
+    const long t0 = lo[1] + (long)b * (L.ty - 1);
+    if (!(t0 - 3 < 0 || t0 + L.ty - 1 + 2 >= ny)) oky++;
+  }
+  return 1.0 - ((double)okx / L.gx) * ((double)oky / L.gy);
+}
+
 }  // namespace eb

@@ -138,7 +138,7 @@ EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
 // handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
 // i.e. of cell (i,j,k) itself.
-template <bool GEN, class Emit>
+template <bool GEN, bool AG, class Emit>
 EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
   StencilPt pt[6];
@@ -170,12 +170,26 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     s.srL = P.aux[3][pt[2].off];
     s.srR = P.aux[3][pt[3].off];
   } else {
+    // Tiles that touch a boundary (AG instantiation, chosen for launches where such tiles are
+    // many: thin grids, small grids, the boundary shells of a decomposed run): owned points, and
+    // ghost points that are an owned cell with at most its momenta negated (periodic wrap, Neumann,
+    // reflecting: 1/rho, p, c, sqrt(rho) are even in the momenta), still read the per-cell arrays;
+    // only Dirichlet ghosts (rho, e_t negated) and halo-slab points are derived here.
+    const bool have_aux = AG && P.aux[0] != nullptr;
 #pragma unroll
     for (int l = 0; l < 6; l++) {
-      const CellAux a = cell_aux(P.gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
-      s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
-      if (l == 2) s.srL = a.sr;
-      if (l == 3) s.srR = a.sr;
+      if (have_aux && pt[l].src < 0 && (pt[l].neg & 0x11u) == 0u) {
+        s.rinv[l] = P.aux[0][pt[l].off];
+        s.p[l] = P.aux[1][pt[l].off];
+        s.c[l] = P.aux[2][pt[l].off];
+        if (l == 2) s.srL = P.aux[3][pt[l].off];
+        if (l == 3) s.srR = P.aux[3][pt[l].off];
+      } else {
+        const CellAux a = cell_aux(P.gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
+        s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
+        if (l == 2) s.srL = a.sr;
+        if (l == 3) s.srR = a.sr;
+      }
     }
   }
 
@@ -248,10 +262,10 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   return bits;
 }
 
-template <class Emit>
+template <bool AG, class Emit>
 EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
-  return gen ? face_all<true>(P, dir, i, j, k, emit) : face_all<false>(P, dir, i, j, k, emit);
+  return gen ? face_all<true, AG>(P, dir, i, j, k, emit) : face_all<false, AG>(P, dir, i, j, k, emit);
 }
 
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
@@ -300,7 +314,8 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // plane, so their load bursts and FP64 stretches overlap.
 // GW: the forcing is not the per-field constant of the config; the caller has run the
 // external_forces hook into wdot (utilities.cpp:65) and every store is wdot = wdot - div.
-template <int MAXT, int MINB, bool GW = false>
+// AG: boundary tiles read the per-cell arrays wherever they are valid (see face_all).
+template <int MAXT, int MINB, bool GW = false, bool AG = false>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
@@ -336,17 +351,17 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
   // z-face below the first plane of the segment
   if (owns)
-    face_dispatch(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
+    face_dispatch<AG>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
                   [&](int v, double x) { ZLO[v * TR] = x; });
 
   for (long k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (need_x) {
-      const int bits = face_dispatch(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
+      const int bits = face_dispatch<AG>(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
       if (owns) mask |= bits;
     }
     if (need_y)
-      face_dispatch(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
+      face_dispatch<AG>(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
     if (pair) {
       if (ty > 0) eb_bar_sync(ty, 64);
       if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
     if (owns) {
       const long cell = i + P.nx * (j + P.ny * k);
-      face_dispatch(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
+      face_dispatch<AG>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
                     [&](int v, double zup) {
                       const double div = ((FX[v * TR + 1] - FX[v * TR]) * P.rdx
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)

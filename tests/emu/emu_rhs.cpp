@@ -8,7 +8,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot)
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -48,7 +48,9 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.pair_sync = L.pair;
   if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
   P.seg_len = L.seg_len;
-  if (g_in_wdot) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, true>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+  // the three instantiations launch_box() chooses from on the device
+  if (g_in_wdot) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, true, false>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+  else if (aux_in_gen) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, false, true>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
   else cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
   *state_bits = flag;
   return flag ? -1 : 0;

@@ -1,4 +1,5 @@
-"""The external_forces hook in full generality on the device: forcing that
+"""Late additions of round 1 (written after its last GPU session, hence sorted last): (1) the
+external_forces hook in full generality on the device: forcing that
 depends on position and time is run into wdot before the evaluation, as the reference's fEuler
 does (utilities.cpp:28,65), and the kernel computes wdot = wdot - div F(w)
 (eulerb200_set_forcing_in_wdot).  fEuler is affine in G and the reference rounds G - div once, so
@@ -69,3 +70,22 @@ def test_dropin_with_a_varying_hook_against_the_reference(pkg, nvar):
     print(res.stdout, res.stderr)
     assert res.returncode == 0 and "DROPIN_CHECK PASS" in res.stdout, res.stdout + res.stderr
     assert res.stdout.count("run before every evaluation") == 5
+
+
+@pytest.mark.parametrize("n,nchem,bcs", [((16, 12, 10), 2, [R] * 6), ((40, 9, 11), 0, [P, P, R, R, N, N]),
+                                         ((64, 20, 24), 10, [R] * 6), ((3, 40, 36), 6, [N] * 6),
+                                         ((200, 3, 3), 0, [N] * 6), ((70, 34, 40), 3, [P] * 6)])
+def test_boundary_heavy_instantiation_matches_oracle(pkg, oracle_mod, port, monkeypatch, n, nchem, bcs):
+    """EULERB200_KERNEL=1 (opt-in until timed on a B200): launches in which a quarter or more of the
+    tiles touch a boundary run the AG instantiation, where boundary tiles read the per-cell 1/rho, p, c,
+    sqrt(rho) arrays for owned points and for ghost points that only differ in the sign of a momentum
+    instead of re-deriving them for all six stencil points.  Same tolerance as the default kernel."""
+    from helpers import gpu_feuler
+    monkeypatch.setenv("EULERB200_KERNEL", "1")
+    u = make_udata(pkg, n, nchem, bcs, forcing=[0, 0, -0.1, 0, 0])
+    parts = oracle_mod.random_state(n, nchem, seed=sum(n) + nchem)
+    ret, got = gpu_feuler(pkg, u, parts)
+    ret_ref, ref, _ = oracle_feuler(port, u, parts)
+    assert ret == 0 and ret_ref == 0, u.last_error()
+    assert max(normwise_errors(got, ref, rounding_floor(parts, u.gamma, (u.dx, u.dy, u.dz)))) <= 1e-12
+    u.FreeData()

@@ -45,6 +45,27 @@ def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, th
     # same answer with every derived value computed on the fly (no aux arrays)
     ret, got2, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, use_aux=0)
     assert ret == 0 and max(normwise_errors(got2, ref, floor)) <= 1e-12
+    # and with the instantiation for boundary-heavy launches (AG: boundary tiles read the per-cell
+    # arrays for owned points and for ghost points that only differ in the sign of a momentum)
+    ret, got3, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, aux_in_gen=1)
+    assert ret == 0 and max(normwise_errors(got3, ref, floor)) <= 1e-12
+
+
+@pytest.mark.parametrize("bcs", [[D] * 6, [R, R, D, D, N, N], [D, D, P, P, R, R]])
+def test_emulated_boundary_instantiation_with_dirichlet_ghosts(emu, oracle_mod, port, bcs):
+    """AG instantiation: Dirichlet ghosts negate rho and e_t, so their 1/rho, p, c cannot come from
+    the per-cell arrays; the result must equal the default instantiation wherever that is finite
+    (the Dirichlet boundary cells are non-finite in the reference too)."""
+    n, nchem = (34, 9, 8), 2
+    w = oracle_mod.random_state(n, nchem, seed=4)
+    d = (0.1, 0.2, 0.3)
+    ret0, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=128)
+    ret1, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=128, aux_in_gen=1)
+    assert ret0 == ret1
+    for a, b in zip(base, got):
+        fin = np.isfinite(a)
+        assert np.array_equal(fin, np.isfinite(b))
+        assert np.abs(a[fin] - b[fin]).max() <= 1e-12 * np.abs(a[fin]).max()
 
 
 @pytest.mark.parametrize("n,nchem,bcs,threads", [
@@ -143,7 +164,8 @@ def test_emulated_two_rank_split_with_halo_buffers_and_subboxes(emu, pkg, oracle
         hi = [nl[a] - (3 if b["nbr"][2 * a + 1] not in (NO, rank) else 0) for a in range(3)]
         boxes = [(lo, hi), ([0, lo[1], lo[2]], [lo[0], hi[1], hi[2]]), ([hi[0], lo[1], lo[2]], [nl[0], hi[1], hi[2]])]
         for blo, bhi in boxes:
-            ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi)
+            ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi,
+                                      aux_in_gen=1 if blo[0] != lo[0] or bhi[0] != hi[0] else 0)   # shells: AG
             assert ret == 0
             for o, p_ in zip(out, part):
                 m = ~np.isnan(p_)
@@ -180,3 +202,6 @@ def test_emulated_slow_mode_matches_reference_sequence(emu, oracle_mod, port):
     zeros = [np.zeros_like(x) for x in got]
     ret, got_gw, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, energy_units=eu, g_in_wdot=zeros)
     assert ret == 0 and all(np.array_equal(a, b) for a, b in zip(got, got_gw))
+    # and the boundary-heavy instantiation
+    ret, got_ag, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, energy_units=eu, aux_in_gen=1)
+    assert ret == 0 and max(normwise_errors(got_ag, ref, floor)) <= 1e-12
