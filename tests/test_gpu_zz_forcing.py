@@ -3,8 +3,8 @@ external_forces hook in full generality on the device: forcin
 depends on position and time is run into wdot before the evaluation, as the reference's fEuler
 does (utilities.cpp:28,65), and the kernel computes wdot = wdot - div F(w)
 (eulerb200_set_forcing_in_wdot).  fEuler is affine in G and the reference rounds G - div once, so
-the expected result is exactly G + (oracle with zero forcing).  Tolerance 1e-12 normwise.
-(Named to sort last: added after the last GPU session of round 1.)"""
+the expected result is exactly G + (oracle with zero forcing); (2) the AG instantiation of the
+fused kernel for boundary-heavy launches (EULERB200_KERNEL=1).  Tolerance 1e-12 normwise."""
 import os
 import subprocess
 
