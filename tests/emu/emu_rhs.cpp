@@ -61,3 +61,9 @@ extern "C" int emu_decompose(int nprocs, int rank, const int64_t* n, const int32
 {
   return eb::decompose(nprocs, rank, n, bc, dims, coords, ext, nbr);
 }
+
+extern "C" double emu_boundary_tile_fraction(const long* lo, const long* hi, long nx, long ny, int nchem, int threads)
+{
+  const eb::LaunchGeom L = eb::launch_geom(lo, hi, nchem, threads, 2);
+  return eb::boundary_tile_fraction(lo, hi, nx, ny, L);
+}

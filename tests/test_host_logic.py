@@ -121,3 +121,23 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_boundary_tile_fraction_of_the_baseline_shapes(pkg):
+    """launch_box() offers the AG instantiation (EULERB200_KERNEL=1) to launches in which a quarter or
+    more of the tiles touch a boundary: not the 512^3 bench shape (its SASS stays the measured one),
+    but 256^3, the thin hurricane plane and the 3-cell boundary shells of a decomposed run."""
+    import ctypes as C
+    from emu.emu import build
+    lib = C.CDLL(build())
+    lib.emu_boundary_tile_fraction.restype = C.c_double
+    L3 = C.c_long * 3
+
+    def frac(lo, hi, n, nchem):
+        return lib.emu_boundary_tile_fraction(L3(*lo), L3(*hi), C.c_long(n[0]), C.c_long(n[1]), nchem, 384)
+
+    assert 0.10 < frac((0, 0, 0), (512, 512, 512), (512, 512, 512), 10) < 0.20
+    assert 0.25 <= frac((0, 0, 0), (256, 256, 256), (256, 256, 256), 0) < 0.40
+    assert frac((0, 0, 0), (3, 4096, 4096), (3, 4096, 4096), 0) == 1.0
+    assert frac((0, 3, 3), (3, 509, 509), (512, 512, 512), 10) == 1.0          # x-low shell of an 8-GPU run
+    assert frac((3, 3, 3), (509, 509, 509), (512, 512, 512), 10) < 0.20         # its interior box
