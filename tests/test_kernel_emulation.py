@@ -205,3 +205,106 @@ def test_emulated_slow_mode_matches_reference_sequence(emu, oracle_mod, port):
     # and the boundary-heavy instantiation
     ret, got_ag, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, energy_units=eu, aux_in_gen=1)
     assert ret == 0 and max(normwise_errors(got_ag, ref, floor)) <= 1e-12
+
+
+def test_emulated_random_configurations(emu, oracle_mod, port):
+    """Seeded sweep over grid shapes (thin, ragged, multi-tile), species counts, boundary-condition
+    mixes, CTA sizes, row-synchronisation modes and kernel instantiations: 150 small cases against the
+    oracle, tolerance as everywhere (Dirichlet mixes: same non-finite cells as the oracle, finite cells
+    to 1e-9 of the field's scale -- the neighbourhood of a Dirichlet face is ill-conditioned)."""
+    rng = np.random.default_rng(20261017)
+    for case in range(150):
+        n = tuple(int(x) for x in rng.integers(3, [70, 30, 20]))
+        nchem = int(rng.integers(0, 6))
+        bcs = []
+        for _ in range(3):
+            k = int(rng.choice([P, N, R, D], p=[0.35, 0.3, 0.3, 0.05]))
+            bcs += [P, P] if k == P else [k, int(rng.choice([N, R, D], p=[0.5, 0.45, 0.05]))]
+        threads = int(rng.choice([64, 128, 256, 384]))
+        kw = dict(forcing=[0, 0.3, -0.1, 0, 0.2], threads=threads, pair=int(rng.integers(0, 3)),
+                  aux_in_gen=int(rng.integers(0, 2)), use_aux=int(rng.integers(0, 2)))
+        w = oracle_mod.random_state(n, nchem, seed=int(rng.integers(1, 1000)))
+        d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+        ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, **kw)
+        if ret == -77:                      # rows are not warps: CTA-wide barriers
+            kw["pair"] = 0
+            ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, **kw)
+        ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=kw["forcing"]), w)
+        tag = (case, n, nchem, bcs, kw)
+        if D in bcs:
+            for a, b in zip(got, ref):
+                if a is None:
+                    continue
+                fin = np.isfinite(b)
+                assert np.array_equal(fin, np.isfinite(a)), tag
+                if fin.any():
+                    assert np.abs(a[fin] - b[fin]).max() <= 1e-9 * np.abs(b[fin]).max(), tag
+        else:
+            assert ret == 0 and ret_ref == 0 and bits == 0, tag
+            assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12, tag
+
+
+def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
+    """Seeded sweep of the N>1 kernel path without GPUs: 60 random grids / BC mixes split over 2, 4
+    or 8 ranks the way SetupDecomp does (splits along every axis, periodic wraps onto other ranks),
+    every rank reading its neighbours' packed layers (wire layout of euler3D.hpp:648,696,744) as
+    halo buffers and evaluating interior box and the six boundary slabs as separate sub-box launches
+    exactly like eulerb200_rhs_async; the assembled result against the single-rank oracle on the
+    global grid (the decomposed result is the single-rank result)."""
+    rng = np.random.default_rng(8)
+    d = (0.1, 0.2, 0.3)
+    done = 0
+    while done < 60:
+        world = int(rng.choice([2, 4, 8]))
+        n = tuple(int(x) for x in rng.integers([6, 6, 6], [40, 30, 24]))
+        nchem = int(rng.integers(0, 4))
+        bcs = []
+        for _ in range(3):
+            k = int(rng.choice([P, N, R], p=[0.4, 0.3, 0.3]))
+            bcs += [P, P] if k == P else [k, int(rng.choice([N, R]))]
+        threads, ag = int(rng.choice([64, 128, 256])), int(rng.integers(0, 2))
+        layout = [pkg.dims_and_extents(world, r, n, bcs) for r in range(world)]
+        if any(rc != 0 for rc, *_ in layout):
+            continue                              # some local extent < 3: SetupDecomp refuses
+        done += 1
+        w = oracle_mod.random_state(n, nchem, seed=int(rng.integers(1, 1000)))
+        ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+        shape = (n[2], n[1], n[0])
+        W3 = [w[f].reshape(shape) for f in range(5)] + ([w[5].reshape(shape + (nchem,))] if nchem else [])
+        R3 = [ref[f].reshape(shape) for f in range(5)] + ([ref[5].reshape(shape + (nchem,))] if nchem else [])
+        blocks = []
+        for rc, dims, coords, ext, nbr in layout:
+            sl = (slice(ext[4], ext[5] + 1), slice(ext[2], ext[3] + 1), slice(ext[0], ext[1] + 1))
+            parts = [np.ascontiguousarray(a[sl]).ravel() for a in W3] + ([] if nchem else [None])
+            blocks.append(dict(nbr=nbr, parts=parts, sl=sl, nl=(ext[1] - ext[0] + 1, ext[3] - ext[2] + 1, ext[5] - ext[4] + 1)))
+        for rank, b in enumerate(blocks):
+            recv = [None] * 6
+            for f in range(6):
+                o = b["nbr"][f]
+                if o not in (NO, rank):
+                    recv[f] = port.pack_send(port.cfg(blocks[o]["nl"], nchem, d, 1.4, bcs), blocks[o]["parts"], f ^ 1)
+            nl = b["nl"]
+            Nl = nl[0] * nl[1] * nl[2]
+            out = [np.full(Nl, np.nan) for _ in range(5)] + ([np.full(Nl * nchem, np.nan)] if nchem else [])
+            lo = [3 if b["nbr"][2 * a] not in (NO, rank) else 0 for a in range(3)]
+            hi = [nl[a] - (3 if b["nbr"][2 * a + 1] not in (NO, rank) else 0) for a in range(3)]
+            if any(hi[a] <= lo[a] for a in range(3)):
+                boxes = [([0, 0, 0], list(nl))]      # no interior: one launch after the exchange
+            else:
+                boxes = [(lo, hi), ([0, 0, 0], [nl[0], nl[1], lo[2]]), ([0, 0, hi[2]], list(nl)),
+                         ([0, 0, lo[2]], [nl[0], lo[1], hi[2]]), ([0, hi[1], lo[2]], [nl[0], nl[1], hi[2]]),
+                         ([0, lo[1], lo[2]], [lo[0], hi[1], hi[2]]), ([hi[0], lo[1], lo[2]], [nl[0], hi[1], hi[2]])]
+            tag = (n, nchem, bcs, world, rank, threads, ag)
+            for blo, bhi in boxes:
+                if any(bhi[a] <= blo[a] for a in range(3)):
+                    continue
+                ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi,
+                                          threads=threads, aux_in_gen=ag)
+                assert ret == 0, tag
+                for o_, p_ in zip(out, part):
+                    m = ~np.isnan(p_)
+                    assert np.all(np.isnan(o_[m])), tag          # boxes do not overlap
+                    o_[m] = p_[m]
+            want = [np.ascontiguousarray(a[b["sl"]]).ravel() for a in R3]
+            assert not any(np.isnan(o_).any() for o_ in out), tag
+            assert max(normwise_errors(out, want)) <= 1e-12, tag
