@@ -190,12 +190,30 @@ struct Stepper {
 
 }  // namespace
 
+// --help: what this driver understands of the reference's input keys (io.cpp:120-222 prints the
+// reference's own list; keys of the implicit / multirate solvers have no meaning here)
+static void usage()
+{
+  printf("euler3d_b200 -f <input file> [--key=value ...]      (keys as in the reference's input files)\n\n"
+         "problem     --problem=<name>   sod_x|sod_y|sod_z, linear_advection_x|_y|_z, rayleigh_taylor,\n"
+         "                               hurricane_xy|_yz|_zx, fluid_blast, primordial_blast\n"
+         "            --nchem=<int>      advected species (the reference's compile-time NVAR - 5), 0..64\n"
+         "grid        --nx --ny --nz, --xl --xr --yl --yr --zl --zr, --gamma\n"
+         "            --xlbc --xrbc --ylbc --yrbc --zlbc --zrbc   0 periodic, 1 Neumann, 2 Dirichlet, 3 reflecting\n"
+         "units       --MassUnits --LengthUnits --TimeUnits\n"
+         "run         --t0 --tf --nout, --showstats=1, --output=1 (write output-<n>.eb200), --restart=<n>\n"
+         "stepping    --order=2|3|4|5  or  --order=0 --etable=0|1|3|6|7|8|12   (order overrides etable)\n"
+         "            --rtol --atol --fixedstep=1 --hmax (the fixed step) --hmin --h0 --cfl --mxsteps --maxnef\n"
+         "            --safety --bias --growth --k1 --k2 --k3 --etamx1 --etamxf   (0: ARKODE's default)\n");
+}
+
 int main(int argc, char** argv)
 {
   Inputs in;
   std::vector<std::string> overrides;
   for (int a = 1; a < argc; a++) {
     const std::string s = argv[a];
+    if (s == "--help" || s == "-h") { usage(); return 0; }
     if (s == "-f" && a + 1 < argc) {
       std::ifstream fin(argv[++a]);
       if (!fin) { fprintf(stderr, "cannot open input file %s\n", argv[a]); return 1; }
@@ -218,6 +236,16 @@ int main(int argc, char** argv)
   const int nout = (int)in.get("nout", 10), showstats = (int)in.get("showstats", 0);
   const int write_files = (int)in.get("output", 0), restart = (int)in.get("restart", -1);
   if (P.nchem < 0 || P.nchem > 64) { fprintf(stderr, "illegal nchem = %d\n", P.nchem); return 1; }
+  Table table;
+  if (!make_table((int)in.get("order", 4), (int)in.get("etable", -1), table)) {
+    fprintf(stderr, "\nERROR: no explicit Butcher table for order = %d / etable = %d (orders 2-5; table ids 0 1 3 6 7 8 12)\n\n",
+            (int)in.get("order", 4), (int)in.get("etable", -1));
+    return 1;
+  }
+  if (!table.embedded && (int)in.get("fixedstep", 0) == 0) {
+    fprintf(stderr, "\nERROR: this Butcher table has no embedding: it needs fixedstep = 1\n\n");
+    return 1;
+  }
 
   eulerb200_config cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -249,18 +277,10 @@ int main(int argc, char** argv)
   const long N = P.nx * P.ny * P.nz;
   Stepper S;
   S.ctx = ctx;
-  if (!make_table((int)in.get("order", 4), (int)in.get("etable", -1), S.T)) {
-    fprintf(stderr, "\nERROR: no explicit Butcher table for order = %d / etable = %d (orders 2-5; table ids 0 1 3 6 7 8 12)\n\n",
-            (int)in.get("order", 4), (int)in.get("etable", -1));
-    return 1;
-  }
+  S.T = table;
   S.nglobal = (5 + P.nchem) * N;
   S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
   S.fixedstep = (int)in.get("fixedstep", 0);
-  if (!S.T.embedded && !S.fixedstep) {
-    fprintf(stderr, "\nERROR: this Butcher table has no embedding: it needs fixedstep = 1\n\n");
-    return 1;
-  }
   S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
   S.cfl = in.get("cfl", 0);
   S.mxsteps = (int)in.get("mxsteps", 5000);

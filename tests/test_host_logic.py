@@ -141,3 +141,16 @@ def test_boundary_tile_fraction_of_the_baseline_shapes(pkg):
     assert frac((0, 0, 0), (3, 4096, 4096), (3, 4096, 4096), 0) == 1.0
     assert frac((0, 3, 3), (3, 509, 509), (512, 512, 512), 10) == 1.0          # x-low shell of an 8-GPU run
     assert frac((3, 3, 3), (509, 509, 509), (512, 512, 512), 10) < 0.20         # its interior box
+
+
+def test_native_driver_help_and_option_errors_need_no_gpu(pkg):
+    """euler3d_b200 --help, and the Butcher-table option checks (order overrides etable,
+    euler3D_main.cpp:207-213), happen before the device is touched."""
+    import subprocess
+    exe = os.path.join(ROOT, "sundials-manyvector-demo_b200", "euler3d_b200")
+    out = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--etable=0|1|3|6|7|8|12" in out.stdout and "primordial_blast" in out.stdout
+    for args, msg in ((["--order=7"], "no explicit Butcher table"), (["--order=0", "--etable=13"], "no explicit Butcher table"),
+                      (["--order=0", "--etable=12"], "needs fixedstep = 1")):
+        out = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert out.returncode == 1 and msg in out.stderr, (args, out.stderr)
