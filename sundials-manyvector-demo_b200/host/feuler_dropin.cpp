@@ -24,12 +24,14 @@
 // kernel subtracts the flux divergence from what it finds there
 // (eulerb200_set_forcing_in_wdot).
 //
-// Multi-rank: the NCCL id (MPI_Bcast) and the CUDA-IPC mailbox handles of the peer-store halo
-// transport (MPI_Allgather) travel once, at context creation, over the reference's own
-// communicator udata->comm -- no MPI call is left on the per-RHS path.
+// Multi-rank: the NCCL id (MPI_Bcast) and, with EULERB200_HALO=p2p, the CUDA-IPC mailbox handles of
+// the peer-store halo transport (MPI_Allgather) travel once, at context creation, over the
+// reference's own communicator udata->comm -- no MPI call is left on the per-RHS path.
 // ---------------------------------------------------------------------------
 #include <euler3D.hpp>
+#include <cstdlib>
 #include <map>
+#include <string>
 #include <vector>
 #include "eulerb200.h"
 
@@ -109,19 +111,23 @@ eulerb200_ctx* context_for(EulerData* udata)
       cerr << "\neulerb200_comm_attach failed: " << eulerb200_last_error(ctx) << "\n\n";
       return NULL;
     }
-    // peer-store halo transport (CUDA IPC over NVLink) when every rank can map its neighbours;
-    // otherwise the context keeps the NCCL send/recv pairs
-    std::vector<char> blobs((size_t)EULERB200_P2P_BLOB_BYTES * udata->nprocs);
-    char mine[EULERB200_P2P_BLOB_BYTES];
-    int ok = eulerb200_p2p_export(ctx, mine) == 0 ? 1 : 0;
-    if (MPI_Allgather(mine, EULERB200_P2P_BLOB_BYTES, MPI_BYTE, blobs.data(), EULERB200_P2P_BLOB_BYTES, MPI_BYTE,
-                      udata->comm) != MPI_SUCCESS) return NULL;
-    double flag = (ok && eulerb200_p2p_attach(ctx, blobs.data()) == 0) ? 1.0 : 0.0;
-    if (MPI_Allreduce(MPI_IN_PLACE, &flag, 1, MPI_DOUBLE, MPI_MIN, udata->comm) != MPI_SUCCESS) return NULL;
-    if (flag == 0.0) {
-      cerr << "\neulerb200: peer-store halo transport unavailable on some rank; this build expects all GPUs of "
-              "the run to be peer-accessible (one NVSwitch node)\n\n";
-      return NULL;
+    // Halo transport: NCCL send/recv pairs by default (fastest at 8 GPUs).  With
+    // EULERB200_HALO=p2p on every rank the peer-store transport (CUDA IPC over NVLink) is attached
+    // instead; it needs every neighbour to be peer-accessible (one NVSwitch node).
+    const char* halo = getenv("EULERB200_HALO");
+    if (halo != NULL && std::string(halo) == "p2p") {
+      std::vector<char> blobs((size_t)EULERB200_P2P_BLOB_BYTES * udata->nprocs);
+      char mine[EULERB200_P2P_BLOB_BYTES];
+      int ok = eulerb200_p2p_export(ctx, mine) == 0 ? 1 : 0;
+      if (MPI_Allgather(mine, EULERB200_P2P_BLOB_BYTES, MPI_BYTE, blobs.data(), EULERB200_P2P_BLOB_BYTES, MPI_BYTE,
+                        udata->comm) != MPI_SUCCESS) return NULL;
+      double flag = (ok && eulerb200_p2p_attach(ctx, blobs.data()) == 0) ? 1.0 : 0.0;
+      if (MPI_Allreduce(MPI_IN_PLACE, &flag, 1, MPI_DOUBLE, MPI_MIN, udata->comm) != MPI_SUCCESS) return NULL;
+      if (flag == 0.0) {
+        cerr << "\neulerb200: EULERB200_HALO=p2p but the peer-store halo transport is unavailable on some rank "
+                "(all GPUs of the run must be peer-accessible); unset it to use NCCL\n\n";
+        return NULL;
+      }
     }
   }
   if (probe == 1 && eulerb200_set_forcing_in_wdot(ctx, 1) != 0) return NULL;
