@@ -1,15 +1,17 @@
 // ---------------------------------------------------------------------------
 // emu_abi.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE, never shipped or loaded by the product.
 //
-// The handful of C-ABI entry points (include/eulerb200.h) that the drop-in fEuler / stability of
-// sundials-manyvector-demo_b200/host/feuler_dropin.cpp calls, implemented on top of the CPU
-// emulation of the kernel SOURCE (emu_rhs.cpp), single rank.  It exists so that the "not gpu"
+// The C-ABI entry points (include/eulerb200.h) that the drop-in fEuler / stability of
+// sundials-manyvector-demo_b200/host/feuler_dropin.cpp and the native driver host/euler3d_b200.cpp
+// call, implemented on top of the CPU emulation of the kernel SOURCE (emu_rhs.cpp), single rank.  It exists so that the "not gpu"
 // tier can link the drop-in against the reference's own EulerData and run it next to the
 // unmodified reference fEuler (oracle/dropin_check.cpp) without a GPU: that checks the host
 // logic of the drop-in (probe of the external_forces hook, per-call hook, pointer plumbing,
 // error paths), nothing about the device library.
 // ---------------------------------------------------------------------------
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include "../../include/eulerb200.h"
 
@@ -17,7 +19,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
                        int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen);
 
-struct eulerb200_ctx { eulerb200_config cfg; bool gw; std::string err; };
+struct eulerb200_ctx { eulerb200_config cfg; bool gw; std::string err; long launches; };
 static std::string g_err;
 
 extern "C" {
@@ -25,7 +27,7 @@ int eulerb200_version(void) { return EULERB200_VERSION; }
 int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
 {
   if (!cfg || !out || cfg->nranks != 1) { g_err = "emu_abi: single rank only"; return -1; }
-  *out = new eulerb200_ctx{*cfg, false, ""};
+  *out = new eulerb200_ctx{*cfg, false, "", 0};
   return 0;
 }
 int eulerb200_destroy(eulerb200_ctx* c) { delete c; return 0; }
@@ -52,6 +54,50 @@ int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl
     alpha = alpha < x ? x : alpha;
   }
   *dt_stab = cfl * std::fmin(std::fmin(c->cfg.dx, c->cfg.dy), c->cfg.dz) / alpha;
+  return 0;
+}
+// what the native driver (host/euler3d_b200.cpp) needs on top: "device" memory is host memory here
+int eulerb200_rhs(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* s)
+{
+  c->launches += 2;
+  return eulerb200_rhs_any(c, t, w, wdot, s);
+}
+int eulerb200_stability(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void* s)
+{
+  return eulerb200_stability_any(c, w, cfl, dt_stab, s);
+}
+void* eulerb200_device_alloc(int64_t bytes) { return bytes > 0 ? malloc((size_t)bytes) : nullptr; }
+void eulerb200_device_free(void* p) { free(p); }
+int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
+int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
+int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
+// lincomb_kernel / wrms_kernel of eulerb200.cu, same expressions (the sum order of the norm differs)
+int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x, double* out,
+                          int64_t n, void*)
+{
+  if (!c || nterms < 1 || nterms > 8) return -1;
+  for (int64_t i = 0; i < n; i++) {
+    double s = coef[0] * x[0][i];
+    for (int t = 1; t < nterms; t++) s = std::fma(coef[t], x[t][i], s);
+    out[i] = s;
+  }
+  c->launches++;
+  return 0;
+}
+int eulerb200_vec_wrms(eulerb200_ctx* c, const double* const* x, const double* const* y, double rtol, double atol,
+                       int64_t nglobal, double* result, void*)
+{
+  const int64_t N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
+  double acc = 0.0;
+  for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++) {
+    const int64_t len = f < 5 ? N : N * c->cfg.nchem;
+    for (int64_t i = 0; i < len; i++) {
+      const double q = x[f][i] / std::fma(rtol, std::fabs(y[f][i]), atol);
+      acc = std::fma(q, q, acc);
+    }
+    c->launches++;
+  }
+  *result = std::sqrt(acc / (double)nglobal);
   return 0;
 }
 // multi-rank entry points the drop-in references but never reaches with one rank

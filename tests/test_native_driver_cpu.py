@@ -1,0 +1,95 @@
+"""The native explicit driver (host/euler3d_b200.cpp) on the CPU tier: linked against the CPU
+emulation of the kernel source (tests/emu/emu_abi.cpp, test infrastructure) instead of
+libeulerb200.so, it runs small problems end to end without a GPU -- input parsing, problem
+plug-ins, Butcher tables, step loop, diagnostics text, solution files -- and must reproduce the
+Python driver driven by the CPU oracle.  The device library itself is exercised by
+tests/test_gpu_native_driver.py."""
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import NpVec, OracleVecOps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+P, N, D, R = 0, 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    d = tmp_path_factory.mktemp("native_emu")
+    objs = []
+    for src, flags in (("emu_rhs.cpp", ["-O1", "-ffp-contract=off"]), ("emu_abi.cpp", ["-O1"])):
+        obj = str(d / (src + ".o"))
+        subprocess.check_call(["g++", "-std=c++14", "-w", "-c"] + flags + ["-o", obj, os.path.join(HERE, "emu", src)])
+        objs.append(obj)
+    out = str(d / "euler3d_emu")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-o", out,
+                           os.path.join(ROOT, "sundials-manyvector-demo_b200", "host", "euler3d_b200.cpp")] + objs)
+    return out
+
+
+def run(exe, args, cwd):
+    res = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, cwd=str(cwd))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    return res.stdout
+
+
+def advection_state(n, axis):
+    d = [1.0 / n[0], 1.0 / n[1], 1.0 / n[2]]
+    idx = np.arange(n[0] * n[1] * n[2])
+    c = [(idx % n[0] + 0.5) * d[0], ((idx // n[0]) % n[1] + 0.5) * d[1], (idx // (n[0] * n[1]) + 0.5) * d[2]]
+    rho = 1.0 + 0.1 * np.sin(2 * math.pi * c[axis])
+    m = [0.5 * rho if a == axis else np.zeros_like(rho) for a in range(3)]
+    et = 1.0 / 0.4 + 0.5 * (m[0] ** 2 + m[1] ** 2 + m[2] ** 2) / rho
+    return [rho] + m + [et], d
+
+
+@pytest.mark.parametrize("sel,kw", [(["--order=4"], dict(order=4)), (["--order=3"], dict(order=3)),
+                                    (["--order=0", "--etable=8"], dict(order=0, etable=8)),
+                                    (["--order=0", "--etable=6"], dict(order=0, etable=6)),
+                                    (["--order=0", "--etable=12"], dict(order=0, etable=12))])
+def test_fixed_step_runs_equal_the_python_driver_with_the_oracle_rhs(pkg, port, exe, tmp_path, sel, kw):
+    """linear_advection_y, 3 x 24 x 3, 20 fixed steps with the chosen Butcher table: the state the
+    native driver writes equals the Python driver's (numpy stage arithmetic, oracle fEuler) to 1e-12."""
+    n, h, tf = (3, 24, 3), 0.005, 0.1
+    out = run(exe, ["--problem=linear_advection_y", "--nx=3", "--ny=24", "--nz=3", "--tf=%g" % tf, "--nout=1",
+                    "--fixedstep=1", "--hmax=%g" % h, "--output=1"] + sel, tmp_path)
+    nst = int(re.search(r"Internal solver steps = (\d+)", out).group(1))
+    nfe = int(re.search(r"Fe = (\d+)", out).group(1))
+    parts, d = advection_state(n, 1)
+    ops = OracleVecOps(port, None, n, 0, d, 1.4, [P] * 6)
+    step = pkg.driver.ERKStep(ops, 0.0, NpVec(parts), pkg.driver.ARKODEParameters(fixedstep=1, hmax=h, **kw))
+    assert step.evolve(tf) == (0, tf)
+    assert (nst, nfe) == (step.stats()["nst"], step.stats()["nfe"]) and nst == 20
+    sol = pkg.problems.read_solution(str(tmp_path / pkg.problems.solution_name(1)))
+    assert sol["time"] == pytest.approx(tf) and sol["n"] == n
+    for f, name in enumerate(pkg.problems.dataset_names(0)):
+        ref = step.w.sub[f]
+        assert np.abs(sol[name].ravel() - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1.0), name
+
+
+def test_adaptive_sod_run_prints_the_reference_diagnostics(pkg, port, exe, tmp_path):
+    """sod_x 40 x 3 x 3, adaptive order 4: diagnostics text, counters close to the Python driver's
+    (same loop; the kernel arithmetic differs from the oracle's at 1e-15, which an adaptive run on a
+    shock can turn into a step more or less), conservation while the waves are inside the domain."""
+    out = run(exe, ["--problem=sod_x", "--nx=40", "--ny=3", "--nz=3"] + ["--%s=1" % k for k in
+              ("xlbc", "xrbc", "ylbc", "yrbc", "zlbc", "zrbc")] + ["--tf=0.05", "--nout=2", "--rtol=1e-5", "--atol=1e-10"], tmp_path)
+    errR = [[float(x) for x in m.split()] for m in re.findall(r"errR =\s+(.*)", out)]
+    nst = int(re.search(r"Internal solver steps = (\d+)", out).group(1))
+    assert len(errR) == 3 and errR[0][0] == 0.0 and all(e[2] == 0.0 and e[3] == 0.0 for e in errR)
+    x = (np.arange(360) % 40 + 0.5) / 40
+    rho, p = np.where(x < 0.5, 1.0, 0.125), np.where(x < 0.5, 1.0, 0.1)
+    ops = OracleVecOps(port, None, (40, 3, 3), 0, (1 / 40, 1 / 3, 1 / 3), 1.4, [N] * 6)
+    step = pkg.driver.ERKStep(ops, 0.0, NpVec([rho, np.zeros(360), np.zeros(360), np.zeros(360), p / 0.4]),
+                              pkg.driver.ARKODEParameters(order=4, rtol=1e-5, atol=1e-10))
+    for tout in (0.025, 0.05):
+        assert step.evolve(tout)[0] == 0
+    assert abs(step.stats()["nst"] - nst) <= max(2, 0.05 * nst)
+    sol = pkg.problems.exact_riemann(0.05, list((np.arange(40) + 0.5) / 40), 0.5, 1.4)
+    err = np.sqrt(np.mean((step.w.sub[0] - np.array([s[0] for s in sol])[np.arange(360) % 40]) ** 2))
+    assert errR[-1][0] == pytest.approx(err, rel=3e-3)          # printed with three digits
