@@ -93,3 +93,30 @@ def test_adaptive_sod_run_prints_the_reference_diagnostics(pkg, port, exe, tmp_p
     sol = pkg.problems.exact_riemann(0.05, list((np.arange(40) + 0.5) / 40), 0.5, 1.4)
     err = np.sqrt(np.mean((step.w.sub[0] - np.array([s[0] for s in sol])[np.arange(360) % 40]) ** 2))
     assert errR[-1][0] == pytest.approx(err, rel=3e-3)          # printed with three digits
+
+
+def test_colour_tracers_solution_files_and_restart(pkg, exe, tmp_path):
+    """hurricane_xy with four colour-stripe species (the reference's NVAR = 9 build), fixed step:
+    species statistics in the text, solution files at every output, and a restart from the middle
+    file that ends in the state of the uninterrupted run (io.cpp:716-1150)."""
+    args = ["-f", os.path.join(ROOT, "inputs", "input_hurricane.txt"), "--problem=hurricane_xy", "--nx=12", "--ny=10",
+            "--nz=3", "--nchem=4", "--tf=0.004", "--fixedstep=1", "--hmax=0.0005", "--output=1"]
+    out = run(exe, args + ["--nout=2"], tmp_path)
+    assert "num chemical species: 4" in out and "||c3||" in out
+    assert int(re.search(r"Internal solver steps = (\d+)", out).group(1)) == 8
+    sols = [pkg.problems.read_solution(str(tmp_path / pkg.problems.solution_name(i))) for i in range(3)]
+    assert [s["time"] for s in sols] == [0.0, 0.002, 0.004] and sols[0]["nchem"] == 4 and sols[0]["n"] == (12, 10, 3)
+    stripes = sum(sols[0]["Chemical-%03d" % v] for v in range(4))
+    assert np.array_equal(stripes, np.ones_like(stripes))            # every cell starts in exactly one stripe
+    assert not np.array_equal(sols[2]["Chemical-000"], sols[0]["Chemical-000"])        # and the stripes move
+    again = tmp_path / "again"
+    again.mkdir()
+    (again / pkg.problems.solution_name(1)).write_bytes((tmp_path / pkg.problems.solution_name(1)).read_bytes())
+    out = run(exe, args + ["--nout=1", "--restart=1"], again)
+    assert "restarting from output-0000001.eb200 at t = 0.002" in out
+    re2 = pkg.problems.read_solution(str(again / pkg.problems.solution_name(2)))
+    assert re2["time"] == 0.004
+    for name in pkg.problems.dataset_names(4):
+        assert np.abs(re2[name] - sols[2][name]).max() <= 1e-13 * max(np.abs(sols[2][name]).max(), 1e-300), name
+    res = subprocess.run([exe] + args + ["--nout=1", "--restart=1", "--nx=13"], capture_output=True, text=True, cwd=str(again))
+    assert res.returncode != 0 and "holds a 12 x 10 x 3 grid" in res.stderr
