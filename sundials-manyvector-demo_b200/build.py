@@ -52,7 +52,7 @@ DRIVER = os.path.join(HERE, "euler3d_b200")
 def build_driver(force=False):
     """The native explicit driver (host/euler3d_b200.cpp): plain C++ on top of the C ABI."""
     src = os.path.join(HERE, "host", "euler3d_b200.cpp")
-    deps = [src, os.path.join(HERE, "host", "problems.hpp"), os.path.join(HERE, "host", "erk_tables.hpp"), os.path.join(HERE, "..", "include", "eulerb200.h"), LIB]
+    deps = [src, os.path.join(HERE, "host", "problems.hpp"), os.path.join(HERE, "host", "erk_tables.hpp"), os.path.join(HERE, "host", "erk_stepper.hpp"), os.path.join(HERE, "..", "include", "eulerb200.h"), LIB]
     if not force and os.path.exists(DRIVER) and os.path.getmtime(DRIVER) > max(os.path.getmtime(d) for d in deps):
         return DRIVER
     cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(HERE, "..", "include"), "-o", DRIVER, src,

@@ -31,6 +31,7 @@
 #include "eulerb200.h"
 #include "problems.hpp"
 #include "erk_tables.hpp"
+#include "erk_stepper.hpp"
 
 namespace {
 
@@ -80,17 +81,12 @@ Vec new_vec(long N, int nchem)
 }
 void free_vec(Vec& v) { for (int f = 0; f < v.nsub; f++) eulerb200_device_free(v.sub[f]); }
 
-struct Stepper {
-  eulerb200_ctx* ctx;
-  Table T;
-  Vec w, ytmp, yerr, k[7];
-  long nglobal;
-  double t = 0, h = 0, rtol, atol, hmin = 0, hmax = 0, h0 = 0, cfl = 0;
-  int fixedstep = 0, mxsteps = 5000, maxnef = 7;
-  double safety = 0.96, bias = 1.5, growth = 20.0, k1 = 0.58, k2 = 0.21, k3 = 0.1, etamx1 = 1e4, etamxf = 0.3;
-  double e2 = 1.0, e3 = 1.0;
-  long nst = 0, nst_a = 0, nfe = 0, netf = 0;
-
+// Vector operations of the shared ERK loop (host/erk_stepper.hpp) on device-resident vectors:
+// everything goes through the C ABI.
+struct DeviceOps {
+  typedef ::Vec Vec;
+  eulerb200_ctx* ctx = NULL;
+  long nglobal = 0;
   void die(const char* what) { fprintf(stderr, "\n%s: %s\n\n", what, eulerb200_last_error(ctx)); exit(1); }
   void lincomb(Vec& out, int n, const double* c, Vec* const* v)
   {
@@ -100,93 +96,24 @@ struct Stepper {
       if (eulerb200_vec_lincomb(ctx, n, c, x, out.sub[f], out.len[f], NULL)) die("eulerb200_vec_lincomb");
     }
   }
-  double wrms(const Vec& x, const Vec& y)
+  double wrms(const Vec& x, const Vec& y, double rtol, double atol)
   {
     double r = 0;
     if (eulerb200_vec_wrms(ctx, x.sub, y.sub, rtol, atol, nglobal, &r, NULL)) die("eulerb200_vec_wrms");
     return r;
   }
-  void f(double tt, Vec& y, Vec& out)
+  int rhs(double tt, Vec& y, Vec& out)
   {
-    nfe++;
     if (eulerb200_rhs(ctx, tt, y.sub, out.sub, NULL)) die("fEuler");
+    return 0;
   }
-  double initial_step(double tout)
+  int stability(Vec& w, double, double cfl, double* dt)
   {
-    if (fixedstep) return hmax;
-    if (h0 > 0) return h0;
-    f(t, w, k[0]);
-    const double d0 = wrms(w, w), d1 = wrms(k[0], w);
-    double hh = (d0 > 1e-5 && d1 > 1e-5) ? 0.01 * d0 / d1 : 1e-6;
-    hh = std::min(hh, fabs(tout - t));
-    { const double c[2] = {1.0, hh}; Vec* v[2] = {&w, &k[0]}; lincomb(ytmp, 2, c, v); }
-    f(t + hh, ytmp, k[1]);
-    { const double c[2] = {1.0, -1.0}; Vec* v[2] = {&k[1], &k[0]}; lincomb(yerr, 2, c, v); }
-    const double d2 = wrms(yerr, w) / hh, dm = std::max(d1, d2);
-    const double h1 = dm > 1e-15 ? pow(0.01 / dm, 1.0 / (T.p + 1)) : std::max(1e-6, 1e-3 * hh);
-    return std::min(std::min(100.0 * hh, h1), fabs(tout - t));
-  }
-  double attempt(double hh)
-  {
-    for (int i = 0; i < T.s; i++) {
-      if (i == 0) { f(t, w, k[0]); continue; }
-      double c[8]; Vec* v[8]; int n = 0; double ci = 0;
-      c[n] = 1.0; v[n++] = &w;
-      for (int j = 0; j < i; j++) { ci += T.A[i][j]; if (T.A[i][j] != 0.0) { c[n] = hh * T.A[i][j]; v[n++] = &k[j]; } }
-      lincomb(ytmp, n, c, v);
-      f(t + ci * hh, ytmp, k[i]);
-    }
-    { double c[8]; Vec* v[8]; int n = 0; c[n] = 1.0; v[n++] = &w;
-      for (int j = 0; j < T.s; j++) if (T.b[j] != 0.0) { c[n] = hh * T.b[j]; v[n++] = &k[j]; }
-      lincomb(ytmp, n, c, v); }
-    if (fixedstep) return 0.0;
-    { double c[8]; Vec* v[8]; int n = 0;
-      for (int j = 0; j < T.s; j++) if (T.b[j] != T.bh[j]) { c[n] = hh * (T.b[j] - T.bh[j]); v[n++] = &k[j]; }
-      lincomb(yerr, n, c, v); }
-    return bias * wrms(yerr, w);
-  }
-  double eta_pid(double dsm) const
-  {
-    const double e1 = std::max(dsm, 1e-10), kk = T.q + 1;
-    return safety * pow(e1, -k1 / kk) * pow(e2, k2 / kk) * pow(e3, -k3 / kk);
-  }
-  int evolve(double tout)
-  {
-    if (h == 0.0) h = initial_step(tout);
-    long steps = 0;
-    while (t < tout * (1 - 1e-14) - 1e-300) {
-      if (steps >= mxsteps) return -1;
-      double hh = h;
-      if (hmax > 0 && !fixedstep) hh = std::min(hh, hmax);
-      if (cfl > 0 && !fixedstep) {
-        double dt = 0;
-        if (eulerb200_stability(ctx, w.sub, cfl, &dt, NULL)) die("stability");
-        hh = std::min(hh, dt);
-      }
-      hh = std::min(hh, tout - t);
-      int nef = 0;
-      double dsm = 0;
-      for (;;) {
-        nst_a++;
-        dsm = attempt(hh);
-        if (fixedstep || dsm <= 1.0) break;
-        netf++; nef++;
-        if (nef >= maxnef || hh <= std::max(hmin, 1e-14 * std::max(fabs(t), 1.0))) return -1;
-        hh *= std::min(nef >= 2 ? etamxf : 1.0, std::max(0.1, eta_pid(dsm)));
-      }
-      std::swap(w, ytmp);
-      t += hh; nst++; steps++;
-      if (!fixedstep) {
-        double eta = std::min(eta_pid(dsm), nst == 1 ? etamx1 : growth);
-        if (eta > 1.0 && eta < 1.5) eta = 1.0;
-        e3 = e2; e2 = std::max(dsm, 1e-10);
-        h = std::max(hh * eta, hmin);
-      }
-    }
-    t = tout;
+    if (eulerb200_stability(ctx, w.sub, cfl, dt, NULL)) die("stability");
     return 0;
   }
 };
+typedef ErkStepper<DeviceOps> Stepper;
 
 }  // namespace
 
@@ -276,9 +203,9 @@ int main(int argc, char** argv)
 
   const long N = P.nx * P.ny * P.nz;
   Stepper S;
-  S.ctx = ctx;
+  S.ops.ctx = ctx;
   S.T = table;
-  S.nglobal = (5 + P.nchem) * N;
+  S.ops.nglobal = (5 + P.nchem) * N;
   S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
   S.fixedstep = (int)in.get("fixedstep", 0);
   S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
