@@ -71,6 +71,21 @@ def build_dropin_emu():
     return exe if os.path.exists(exe) else None
 
 
+def build_refmain():
+    """The reference's own main program (euler3D_main.cpp, io.cpp, gopt.cpp, one problem file,
+    all unmodified) with shim/shim_arkstep.cpp in place of ARKODE: refmain_<problem> with the
+    reference fEuler, refmain_dropin_<problem> with OUR drop-in fEuler on the kernel emulation.
+    Returns {name: path} of what exists, building first where the reference tree is present."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "refmain", "REFERENCE=" + REFERENCE_ROOT])
+    out = {}
+    if os.path.isdir(REF_DIR):
+        for f in os.listdir(REF_DIR):
+            if f.startswith("refmain_"):
+                out[f[len("refmain_"):]] = os.path.join(REF_DIR, f)
+    return out
+
+
 def have_ref(nvar=5):
     return os.path.exists(os.path.join(REF_DIR, "libref_nvar%d.so" % nvar))
 

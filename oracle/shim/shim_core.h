@@ -129,6 +129,12 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype, int root, MPI_Comm);
 int MPI_Allgather(const void* in, int incount, MPI_Datatype, void* out, int outcount, MPI_Datatype, MPI_Comm);
 int MPI_Abort(MPI_Comm, int code);
 double MPI_Wtime(void);
+/* what the reference's main programs need on top (euler3D_main.cpp, io.cpp, problem files) */
+static inline int MPI_Init(int*, char***) { return MPI_SUCCESS; }
+static inline int MPI_Finalize(void) { return MPI_SUCCESS; }
+static inline int MPI_Reduce(const void* in, void* out, int count, MPI_Datatype t, MPI_Op op, int /*root*/, MPI_Comm c) {
+  return MPI_Allreduce(in, out, count, t, op, c);     /* every rank gets the result: a superset */
+}
 
 static inline N_Vector N_VMake_MPIManyVector(MPI_Comm, sunindextype nsub, N_Vector* subs, SUNContext) {
   N_Vector v = new shim_NVector_();
@@ -141,6 +147,16 @@ static inline realtype* N_VGetSubvectorArrayPointer_MPIManyVector(N_Vector v, su
   if (!v || i < 0 || i >= v->nsub) return NULL;
   return v->sub[i]->data;
 }
+
+static inline N_Vector N_VGetSubvector_MPIManyVector(N_Vector v, sunindextype i) {
+  return (!v || i < 0 || i >= v->nsub) ? NULL : v->sub[i];
+}
+static inline void N_VScale(realtype c, N_Vector x, N_Vector z) {
+  if (x->nsub > 0) { for (int s = 0; s < x->nsub; s++) N_VScale(c, x->sub[s], z->sub[s]); return; }
+  for (sunindextype i = 0; i < x->length; i++) z->data[i] = c * x->data[i];
+}
+static inline int N_VEnableFusedOps_Serial(N_Vector, booleantype) { return 0; }
+static inline int N_VEnableFusedOps_MPIManyVector(N_Vector, booleantype) { return 0; }
 
 /* ------------------------------- ARKODE -------------------------------- */
 /* Only the enum *types* are needed (class ARKODEParameters, euler3D.hpp:126-172). */

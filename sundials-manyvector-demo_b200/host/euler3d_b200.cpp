@@ -237,8 +237,9 @@ int main(int argc, char** argv)
 
   double mass0 = -1, energy0 = -1;
   int iout_file = restart >= 0 ? restart : 0;
-  auto outputs = [&](double t, int firstlast) {
-    for (int f = 0; f < 5; f++) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N);
+  // the three per-output actions, called in the reference's order (euler3D_main.cpp:304-332,405-424)
+  auto fetch = [&]() { for (int f = 0; f < 5; f++) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N); };
+  auto write_file = [&](double t) {
     if (write_files) {                                        // output_solution, io.cpp:716-930
       if (P.nchem > 0) eulerb200_copy_to_host(host_chem.data(), S.w.sub[5], sizeof(double) * N * P.nchem);
       if (eb_problems::write_solution(eb_problems::solution_name(iout_file), P, t, hf, host_chem.data()) != 0) {
@@ -247,7 +248,24 @@ int main(int argc, char** argv)
       }
       iout_file++;
     }
-    if (analytic) {                                           // output_diagnostics of the problem file
+  };
+  auto diagnostics = [&](double t) {
+    if (P.name.compare(0, 9, "hurricane") == 0) {             // hurricane.cpp:217-334: rho and the momenta
+      double errI[4] = {0, 0, 0, 0}, errR[4] = {0, 0, 0, 0};
+      for (long k = 0; k < P.nz; k++)
+        for (long j = 0; j < P.ny; j++)
+          for (long i = 0; i < P.nx; i++) {
+            double w4[4];
+            eb_problems::hurricane_true(P, t, i, j, k, w4);
+            const long c = i + P.nx * (j + P.ny * k);
+            for (int f = 0; f < 4; f++) {
+              const double e = fabs(w4[f] - host[f][c]);
+              errI[f] = std::max(errI[f], e); errR[f] += e * e;
+            }
+          }
+      printf("     errI = %9.2e  %9.2e  %9.2e  %9.2e\n", errI[0], errI[1], errI[2], errI[3]);
+      printf("     errR = %9.2e  %9.2e  %9.2e  %9.2e\n", sqrt(errR[0] / N), sqrt(errR[1] / N), sqrt(errR[2] / N), sqrt(errR[3] / N));
+    } else if (analytic) {                                           // output_diagnostics of the problem file
       double errI[5] = {0, 0, 0, 0, 0}, errR[5] = {0, 0, 0, 0, 0};
       for (long k = 0; k < P.nz; k++)
         for (long j = 0; j < P.ny; j++)
@@ -264,6 +282,8 @@ int main(int argc, char** argv)
       printf("     errR = %9.2e  %9.2e  %9.2e  %9.2e  %9.2e\n", sqrt(errR[0] / N), sqrt(errR[1] / N),
              sqrt(errR[2] / N), sqrt(errR[3] / N), sqrt(errR[4] / N));
     }
+  };
+  auto stats = [&](double t, int firstlast) {
     if (showstats) {                                          // print_stats (CGS values), io.cpp:552-636
       const double su[5] = {P.DensityUnits(), P.MomentumUnits(), P.MomentumUnits(), P.MomentumUnits(), P.EnergyUnits()};
       if (firstlast == 0) {
@@ -271,6 +291,12 @@ int main(int argc, char** argv)
         for (int v = 0; v < P.nchem; v++) printf(" ||c%d||   ", v);
         printf("   nst\n");
       }
+      if (firstlast != 1) {
+        printf("   ------------------------------------------------------------");
+        for (int v = 0; v < P.nchem; v++) printf("----------");
+        printf("-------\n");
+      }
+      if (firstlast == 2) return;
       printf("  %9.1e", t);
       for (int f = 0; f < 5; f++) {
         double s = 0;
@@ -303,15 +329,22 @@ int main(int argc, char** argv)
 
   printf("\nWriting initial batch of outputs\n");
   if (showstats) conservation();
-  outputs(t0, 0);
+  fetch();
+  write_file(t0);
+  stats(t0, 0);
+  diagnostics(t0);
 
   const double dTout = (tf - t0) / nout;
   double tout = t0 + dTout;
   for (int iout = 0; iout < nout; iout++) {
     if (S.evolve(tout) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
-    outputs(S.t, 1);
+    fetch();
+    diagnostics(S.t);
+    stats(S.t, 1);
+    write_file(S.t);
     tout = std::min(tout + dTout, tf);
   }
+  stats(S.t, 2);
 
   printf("\nFinal Solver Statistics:\n");
   printf("   Internal solver steps = %ld (attempted = %ld)\n", S.nst, S.nst_a);

@@ -81,6 +81,36 @@ inline void exact_riemann(double t, double x, double xI, double g, double& rho, 
   else { rho = rho5; p = p5; u = 0.0; }
 }
 
+// Critical-rotation solution of the hurricane problems (hurricane.cpp:236-303): density and the
+// three momenta of cell (i,j,k) at time t (the reference's diagnostics compare these four fields).
+// In the rotation plane (a,b): inside r < 2 t sqrt(p0') the gas has expanded into a paraboloid,
+// rho = r^2 / (8 A t^2) with m = rho ((a+b), (b-a)) / (2t); outside it still has rho0 and the
+// velocity of a fluid parcel that started on the v0 circle.  p0' = A gamma rho0^(gamma-1).
+inline void hurricane_true(const Problem& P, double t, long i, long j, long k, double w4[4])
+{
+  const double x = (i + 0.5) * P.dx() + P.xl, y = (j + 0.5) * P.dy() + P.yl, z = (k + 0.5) * P.dz() + P.zl;
+  const std::string pl = P.name.substr(P.name.size() - 2);
+  const double a = pl == "xy" ? x : (pl == "zx" ? z : y), b = pl == "xy" ? y : (pl == "zx" ? x : z);
+  const double A = 25.0, rho0 = 1.0;
+  const double p0p = A * P.gamma * pow(rho0, P.gamma - 1.0);
+  double r = sqrt(a * a + b * b);
+  if (r == 0.0) r = 1e-14;
+  const double ca = a / r, sb = b / r;
+  double rho, ma, mb;
+  if (r < 2.0 * t * sqrt(p0p)) {
+    rho = r * r / (8.0 * A * t * t);
+    ma = rho * (a + b) / (2.0 * t);
+    mb = rho * (b - a) / (2.0 * t);
+  } else {
+    const double swirl = sqrt(2.0 * p0p) * sqrt(r * r - 2.0 * t * t * p0p);
+    rho = rho0;
+    ma = rho0 * (2.0 * t * p0p * ca + swirl * sb) / r;
+    mb = rho0 * (2.0 * t * p0p * sb - swirl * ca) / r;
+  }
+  w4[0] = rho; w4[1] = w4[2] = w4[3] = 0.0;
+  if (pl == "xy") { w4[1] = ma; w4[2] = mb; } else if (pl == "zx") { w4[3] = ma; w4[1] = mb; } else { w4[2] = ma; w4[3] = mb; }
+}
+
 // Analytic / initial state of cell (i,j,k) at time t; returns false if the problem has no
 // analytic solution for t > 0 (then only t = t0 is meaningful).
 inline bool state_at(const Problem& P, double t, long i, long j, long k, double w[5])

@@ -293,6 +293,27 @@ def _true_state(problem, t, u, dev):
         m = [rho * vel if ax == a else zero for a in "xyz"]
         et = p / (u.gamma - 1.0) + (m[0] ** 2 + m[1] ** 2 + m[2] ** 2) * 0.5 / rho
         return [rho] + m + [et]
+    if problem.startswith("hurricane"):
+        # critical-rotation solution (hurricane.cpp:236-303): density and the three momenta only.
+        # In the rotation plane (a, b): inside r < 2 t sqrt(p0') a paraboloid rho = r^2 / (8 A t^2)
+        # with m = rho ((a+b), (b-a)) / (2t); outside rho0 and the velocity of a parcel that
+        # started on the v0 circle.  p0' = A gamma rho0^(gamma-1), A = 25, rho0 = 1.
+        pl = problem[-2:]
+        a, b = {"xy": (X, Y), "zx": (Z, X), "yz": (Y, Z)}[pl]
+        A, rho0 = 25.0, 1.0
+        p0p = A * u.gamma * rho0 ** (u.gamma - 1.0)
+        r = torch.sqrt(a * a + b * b)
+        r = torch.where(r == 0, torch.full_like(r, 1e-14), r)
+        ca, sb = a / r, b / r
+        inside = r < 2.0 * t * math.sqrt(p0p)
+        tt = t if t > 0 else 1.0                                   # (inside is empty at t = 0)
+        rho_in = r * r / (8.0 * A * tt * tt)
+        swirl = math.sqrt(2.0 * p0p) * torch.sqrt(torch.clamp(r * r - 2.0 * t * t * p0p, min=0.0))
+        rho = torch.where(inside, rho_in, torch.full_like(r, rho0))
+        ma = torch.where(inside, rho_in * (a + b) / (2.0 * tt), rho0 * (2.0 * t * p0p * ca + swirl * sb) / r)
+        mb = torch.where(inside, rho_in * (b - a) / (2.0 * tt), rho0 * (2.0 * t * p0p * sb - swirl * ca) / r)
+        m = {"xy": [ma, mb, zero], "zx": [mb, zero, ma], "yz": [zero, ma, mb]}[pl]
+        return [rho] + m
     return None
 
 
@@ -304,9 +325,10 @@ def _allreduce(t, op, u, group):
 
 
 def output_diagnostics(problem, t, w, u, group=None, quiet=False):
-    """``output_diagnostics``: errI (max) and errR (RMS) of the five fluid fields against the
-    analytic solution (linear_advection.cpp:168-240, sod.cpp:383-467); None for problems whose
-    reference hook prints nothing."""
+    """``output_diagnostics``: errI (max) and errR (RMS) against the analytic solution -- the five
+    fluid fields for linear advection and Sod (linear_advection.cpp:168-240, sod.cpp:383-467),
+    density and the three momenta for the hurricane problems (hurricane.cpp:217-334); None for
+    problems whose reference hook prints nothing."""
     import torch
     true = _true_state(problem, t, u, w.sub[0].device)
     if true is None:

@@ -35,6 +35,24 @@ def port(oracle_mod):
     return oracle_mod.Port()
 
 
+@pytest.fixture(scope="session")
+def native_emu_exe(tmp_path_factory):
+    """The native driver (host/euler3d_b200.cpp) linked against the CPU emulation of the kernel
+    source instead of libeulerb200.so (tests/emu/emu_abi.cpp): test infrastructure for the CPU tier."""
+    import subprocess
+    here = os.path.join(ROOT, "tests")
+    d = tmp_path_factory.mktemp("native_emu")
+    objs = []
+    for src, flags in (("emu_rhs.cpp", ["-O1", "-ffp-contract=off"]), ("emu_abi.cpp", ["-O1"])):
+        obj = str(d / (src + ".o"))
+        subprocess.check_call(["g++", "-std=c++14", "-w", "-c"] + flags + ["-o", obj, os.path.join(here, "emu", src)])
+        objs.append(obj)
+    out = str(d / "euler3d_emu")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-o", out,
+                           os.path.join(ROOT, "sundials-manyvector-demo_b200", "host", "euler3d_b200.cpp")] + objs)
+    return out
+
+
 EPS = 2.220446049250313e-16
 
 

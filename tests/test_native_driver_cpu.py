@@ -20,17 +20,8 @@ P, N, D, R = 0, 1, 2, 3
 
 
 @pytest.fixture(scope="module")
-def exe(tmp_path_factory):
-    d = tmp_path_factory.mktemp("native_emu")
-    objs = []
-    for src, flags in (("emu_rhs.cpp", ["-O1", "-ffp-contract=off"]), ("emu_abi.cpp", ["-O1"])):
-        obj = str(d / (src + ".o"))
-        subprocess.check_call(["g++", "-std=c++14", "-w", "-c"] + flags + ["-o", obj, os.path.join(HERE, "emu", src)])
-        objs.append(obj)
-    out = str(d / "euler3d_emu")
-    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-o", out,
-                           os.path.join(ROOT, "sundials-manyvector-demo_b200", "host", "euler3d_b200.cpp")] + objs)
-    return out
+def exe(native_emu_exe):
+    return native_emu_exe
 
 
 def run(exe, args, cwd):
@@ -120,3 +111,32 @@ def test_colour_tracers_solution_files_and_restart(pkg, exe, tmp_path):
         assert np.abs(re2[name] - sols[2][name]).max() <= 1e-13 * max(np.abs(sols[2][name]).max(), 1e-300), name
     res = subprocess.run([exe] + args + ["--nout=1", "--restart=1", "--nx=13"], capture_output=True, text=True, cwd=str(again))
     assert res.returncode != 0 and "holds a 12 x 10 x 3 grid" in res.stderr
+
+
+@pytest.mark.parametrize("plane", ["xy", "yz", "zx"])
+def test_hurricane_diagnostics_python_equals_native(pkg, exe, tmp_path, plane):
+    """output_diagnostics of the hurricane problems (density and the three momenta against the
+    critical-rotation solution, hurricane.cpp:217-334): problems.py evaluated on the state the native
+    driver wrote gives the numbers the native driver printed (which tests/test_reference_main_cpu.py
+    shows to be the reference program's)."""
+    import torch
+    n = {"xy": (16, 14, 3), "yz": (3, 16, 14), "zx": (14, 3, 16)}[plane]
+    out = run(exe, ["-f", os.path.join(ROOT, "inputs", "input_hurricane.txt"), "--problem=hurricane_" + plane,
+                    "--nx=%d" % n[0], "--ny=%d" % n[1], "--nz=%d" % n[2], "--tf=0.002", "--nout=1", "--fixedstep=1",
+                    "--hmax=0.0005", "--output=1"], tmp_path)
+    printed = [[float(x) for x in m.split()] for m in re.findall(r"err[IR] =\s+(.*)", out)]
+    assert len(printed) == 4 and all(len(p) == 4 for p in printed)
+    sol = pkg.problems.read_solution(str(tmp_path / pkg.problems.solution_name(1)))
+    u = pkg.EulerData()
+    u.nx, u.ny, u.nz = n
+    pkg.problems.configure("hurricane_" + plane, u)
+    u.dx, u.dy, u.dz = (u.xr - u.xl) / n[0], (u.yr - u.yl) / n[1], (u.zr - u.zl) / n[2]
+    u.nxl, u.nyl, u.nzl = n
+    u.is_ = u.js = u.ks = 0
+    names = pkg.problems.dataset_names(0)
+    w = pkg.ManyVector([torch.from_numpy(np.ascontiguousarray(sol[nm]).ravel().copy()) for nm in names])
+    d = pkg.problems.output_diagnostics("hurricane_" + plane, 0.002, w, u, quiet=True)
+    for got, want in ((d["errI"], printed[2]), (d["errR"], printed[3])):
+        assert len(got) == 4
+        for a, b in zip(got, want):
+            assert a == pytest.approx(b, rel=6e-3, abs=1e-12)          # three printed digits
