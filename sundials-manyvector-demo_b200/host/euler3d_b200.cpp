@@ -318,8 +318,8 @@ int main(int argc, char** argv)
     for (int f = 0; f < 5; f += 4) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N);
     double m = 0, e = 0;
     for (long c = 0; c < N; c++) { m += host[0][c]; e += host[4][c]; }
-    const double vol = P.dx() * P.dy() * P.dz();
-    m *= vol; e *= vol;
+    const double vol = P.dx() * P.dy() * P.dz() * pow(P.LengthUnits, 3);      // CGS totals, io.cpp:522-524
+    m *= vol * P.DensityUnits(); e *= vol * P.EnergyUnits();
     if (mass0 == -1) { printf("   Total mass   = %.16e\n   Total energy = %.16e\n", m, e); mass0 = m; energy0 = e; }
     else {
       printf("   Mass conservation relative change   = %7.2e\n", fabs(m - mass0) / mass0);

@@ -351,7 +351,9 @@ class Conservation:
 
     def __call__(self, t, w, u, group=None, quiet=False):
         import torch
-        tot = torch.stack([w.sub[0].sum(), w.sub[4].sum()]) * (u.dx * u.dy * u.dz)
+        scales = _unit_scales(u)                                  # CGS totals, io.cpp:522-524
+        vol = u.dx * u.dy * u.dz * float(getattr(u, "LengthUnits", 1.0)) ** 3
+        tot = torch.stack([w.sub[0].sum() * (vol * scales[0]), w.sub[4].sum() * (vol * scales[4])])
         tot = _allreduce(tot, "SUM", u, group).cpu().tolist()
         if self.saved is None:
             self.saved = tot
