@@ -89,3 +89,15 @@ def test_adaptive_runs_agree_to_the_integration_tolerance(refmain, native_emu_ex
     assert [l for l in ref if "err" in l and "=  " in l] == [l for l in nat if "err" in l and "=  " in l]
     steps = [int(re.search(r"steps = (\d+)", next(l for l in t if "Internal solver steps" in l)).group(1)) for t in (ref, nat)]
     assert abs(steps[0] - steps[1]) <= 0.05 * steps[0]
+
+
+def test_cfl_limited_run_goes_through_the_stability_hook(refmain, native_emu_exe, tmp_path):
+    """cfl > 0 makes the reference main register `stability` with the integrator
+    (euler3D_main.cpp:271-275); with loose tolerances every step is the CFL step, so the three
+    programs -- reference stability, drop-in stability, native driver -- take the same steps."""
+    common = ["-f", os.path.join(INPUTS, "input_sod.txt"), "--nx=40", "--tf=0.02", "--nout=2", "--cfl=0.2",
+              "--rtol=1e-2", "--atol=1e-2"]
+    ref = report([refmain["sod_x"]] + common, tmp_path)
+    assert any("Internal solver steps = 7 " in l for l in ref)          # 0.2 * dx / alpha ~ 2.3e-3 ... 3e-3
+    assert report([refmain["dropin_sod_x"]] + common, tmp_path) == ref
+    assert report([native_emu_exe] + common, tmp_path) == ref
