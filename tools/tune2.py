@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tuning aid: time combinations of EULERB200_* environment settings on one GPU.
-   python tools/tune2.py --n 256 256 256 --nchem 10 --env "SPLIT=1 VARIANT=1 VARIANT_T=2" "SPLIT=0 VARIANT=1" """
+   python tools/tune2.py --n 256 256 256 --nchem 10 --env "PAIR=2 KERNEL=1" "PAIR=1" "NO_AUX=1" """
 import argparse
 import os
 import sys
