@@ -266,5 +266,13 @@ class ERKStep:
         self.t = tout
         return 0, self.t
 
+    def set_fixed_step(self, h):
+        """``ARKStepSetFixedStep(arkode_mem, h)``: from now on fixed steps of size h (0: back to
+        adaptive).  What the reference main does after the initial transient when ``htrans > 0``
+        (euler3D_main.cpp:345-367)."""
+        self.o.fixedstep = 1 if h != 0.0 else 0
+        self.o.hmax = float(h)
+        self.h = 0.0
+
     def stats(self):
         return {"nst": self.nst, "nst_a": self.nst_a, "nfe": self.nfe, "netf": self.netf}

@@ -131,6 +131,7 @@ static void usage()
          "run         --t0 --tf --nout, --showstats=1, --output=1 (write output-<n>.eb200), --restart=<n>\n"
          "stepping    --order=2|3|4|5  or  --order=0 --etable=0|1|3|6|7|8|12   (order overrides etable)\n"
          "            --rtol --atol --fixedstep=1 --hmax (the fixed step) --hmin --h0 --cfl --mxsteps --maxnef\n"
+         "            --fixedstep=1 --htrans=<t>  adaptive (steps <= hmax) over (t0, t0+htrans], then fixed steps of hmax\n"
          "            --safety --bias --growth --k1 --k2 --k3 --etamx1 --etamxf   (0: ARKODE's default)\n");
 }
 
@@ -169,7 +170,7 @@ int main(int argc, char** argv)
             (int)in.get("order", 4), (int)in.get("etable", -1));
     return 1;
   }
-  if (!table.embedded && (int)in.get("fixedstep", 0) == 0) {
+  if (!table.embedded && ((int)in.get("fixedstep", 0) == 0 || in.get("htrans", 0) > 0)) {
     fprintf(stderr, "\nERROR: this Butcher table has no embedding: it needs fixedstep = 1\n\n");
     return 1;
   }
@@ -207,7 +208,16 @@ int main(int argc, char** argv)
   S.T = table;
   S.ops.nglobal = (5 + P.nchem) * N;
   S.rtol = in.get("rtol", 1e-8); S.atol = in.get("atol", 1e-12);
-  S.fixedstep = (int)in.get("fixedstep", 0);
+  // fixedstep = 0 adaptive, 1 fixed steps of hmax; with htrans > 0 as well: adaptive (steps <= hmax)
+  // over (t0, t0+htrans], fixed afterwards (euler3D_main.cpp:79-88,221,345-367)
+  const double htrans = in.get("htrans", 0);
+  int fixed_mode = (int)in.get("fixedstep", 0);
+  if (fixed_mode && in.get("hmax", 0) <= 0) {
+    fprintf(stderr, "\nError: fixed time stepping requires hmax > 0 (%g given)\n", in.get("hmax", 0));
+    return 1;
+  }
+  if (fixed_mode && htrans > 0) fixed_mode = 2;
+  S.fixedstep = fixed_mode == 1 ? 1 : 0;
   S.hmin = in.get("hmin", 0); S.hmax = in.get("hmax", 0); S.h0 = in.get("h0", 0);
   S.cfl = in.get("cfl", 0);
   S.mxsteps = (int)in.get("mxsteps", 5000);
@@ -334,6 +344,10 @@ int main(int argc, char** argv)
   stats(t0, 0);
   diagnostics(t0);
 
+  if (fixed_mode == 2) {               // initial transient (euler3D_main.cpp:340-367)
+    if (S.evolve(t0 + htrans) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
+    S.fixedstep = 1; S.h = 0.0;         // ARKStepSetFixedStep(hmax)
+  }
   const double dTout = (tf - t0) / nout;
   double tout = t0 + dTout;
   for (int iout = 0; iout < nout; iout++) {

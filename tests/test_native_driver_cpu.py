@@ -140,3 +140,22 @@ def test_hurricane_diagnostics_python_equals_native(pkg, exe, tmp_path, plane):
         assert len(got) == 4
         for a, b in zip(got, want):
             assert a == pytest.approx(b, rel=6e-3, abs=1e-12)          # three printed digits
+
+
+def test_initial_transient_then_fixed_steps_equals_the_python_driver(pkg, port, exe, tmp_path):
+    """fixedstep = 1 with htrans > 0 (euler3D_main.cpp:87-88,345-367): adaptive steps (<= hmax) over
+    (t0, t0+htrans], then ARKStepSetFixedStep(hmax).  Native driver against driver.py + oracle RHS."""
+    n, h, tf, htrans = (3, 24, 3), 0.005, 0.1, 0.02
+    out = run(exe, ["--problem=linear_advection_y", "--nx=3", "--ny=24", "--nz=3", "--tf=%g" % tf, "--nout=1",
+                    "--fixedstep=1", "--hmax=%g" % h, "--htrans=%g" % htrans, "--output=1", "--rtol=1e-6"], tmp_path)
+    nst = int(re.search(r"Internal solver steps = (\d+)", out).group(1))
+    parts, d = advection_state(n, 1)
+    ops = OracleVecOps(port, None, n, 0, d, 1.4, [P] * 6)
+    step = pkg.driver.ERKStep(ops, 0.0, NpVec(parts), pkg.driver.ARKODEParameters(order=4, rtol=1e-6, hmax=h))
+    assert step.evolve(htrans) == (0, htrans)
+    step.set_fixed_step(h)
+    assert step.evolve(tf) == (0, tf)
+    assert step.stats()["nst"] == nst and nst >= 4 + 16
+    sol = pkg.problems.read_solution(str(tmp_path / pkg.problems.solution_name(1)))
+    for f, name in enumerate(pkg.problems.dataset_names(0)):
+        assert np.abs(sol[name].ravel() - step.w.sub[f]).max() <= 1e-12 * max(np.abs(step.w.sub[f]).max(), 1.0), name
