@@ -77,7 +77,7 @@ def build_refmain():
     reference fEuler, refmain_dropin_<problem> with OUR drop-in fEuler on the kernel emulation.
     Returns {name: path} of what exists, building first where the reference tree is present."""
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
-        subprocess.check_call(["make", "-s", "-C", HERE, "refmain", "REFERENCE=" + REFERENCE_ROOT])
+        subprocess.check_call(["make", "-s", "-j4", "-C", HERE, "refmain", "REFERENCE=" + REFERENCE_ROOT])
     out = {}
     if os.path.isdir(REF_DIR):
         for f in os.listdir(REF_DIR):

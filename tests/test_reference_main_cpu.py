@@ -34,6 +34,10 @@ CASES = {
     "hurricane_zx": ("input_hurricane.txt", ["--nx=18", "--ny=3", "--nz=22", "--tf=0.002", "--nout=2", "--fixedstep=1",
                                              "--hmax=0.0005", "--showstats=1"]),
     "sod_z": ("input_sod.txt", ["--nx=3", "--ny=3", "--nz=40", "--tf=0.01", "--nout=2", "--fixedstep=1", "--hmax=0.0005"]),
+    # six colour-stripe species (the reference's NVAR = 11 build): tracer initial condition, species
+    # columns of the statistics table, and the species part of the RHS through the drop-in
+    "hurricane_zx_color": ("input_hurricane.txt", ["--nx=14", "--ny=3", "--nz=12", "--tf=0.002", "--nout=2", "--fixedstep=1",
+                                                   "--hmax=0.0005", "--showstats=1"]),
     # fixedstep with htrans > 0: adaptive (steps <= hmax) over the initial transient, fixed afterwards
     "linear_advection_y": ("input_linear_advection.txt", ["--nx=3", "--ny=24", "--nz=3", "--tf=0.1", "--nout=2",
                                                           "--fixedstep=1", "--hmax=0.005", "--htrans=0.02", "--showstats=1"]),
@@ -79,7 +83,8 @@ def test_reference_main_prints_the_same_with_our_feuler_and_the_native_driver_pr
     assert sum("Total RHS evals" in l for l in ref) == 1
     dropin = report([refmain["dropin_" + problem]] + common, tmp_path)
     assert dropin == ref, "\n".join(dropin) + "\n--- vs reference fEuler ---\n" + "\n".join(ref)
-    native = report([native_emu_exe] + common + ["--problem=" + problem], tmp_path)
+    native_args = ["--problem=hurricane_zx", "--nchem=6"] if problem == "hurricane_zx_color" else ["--problem=" + problem]
+    native = report([native_emu_exe] + common + native_args, tmp_path)
     assert native == ref, "\n".join(native) + "\n--- vs reference main ---\n" + "\n".join(ref)
 
 
