@@ -246,7 +246,7 @@ int main(int argc, char** argv)
   if (P.nchem > 0) eulerb200_copy_to_device(S.w.sub[5], host_chem.data(), sizeof(double) * N * P.nchem);
 
   double mass0 = -1, energy0 = -1;
-  int iout_file = restart >= 0 ? restart : 0;
+  int iout_file = restart >= 0 ? restart : 0, outputs_done = 0;
   // the three per-output actions, called in the reference's order (euler3D_main.cpp:304-332,405-424)
   auto fetch = [&]() { for (int f = 0; f < 5; f++) eulerb200_copy_to_host(host[f].data(), S.w.sub[f], sizeof(double) * N); };
   auto write_file = [&](double t) {
@@ -256,6 +256,14 @@ int main(int argc, char** argv)
         fprintf(stderr, "output_solution: cannot write %s\n", eb_problems::solution_name(iout_file).c_str());
         exit(1);
       }
+      // write_parameters (io.cpp:645-714): an input file that continues this run from the file just
+      // written -- "euler3d_b200 -f restart_parameters.txt"
+      std::ofstream pf("restart_parameters.txt");
+      pf << "# euler3d_b200 restart file\nproblem = " << P.name << "\n";
+      std::map<std::string, double> vals = in.v;
+      vals["t0"] = t; vals["nout"] = nout - outputs_done; vals["h0"] = S.h; vals["restart"] = iout_file; vals["output"] = 1;
+      char buf[64];
+      for (const auto& kv : vals) { snprintf(buf, sizeof buf, "%.17g", kv.second); pf << kv.first << " = " << buf << "\n"; }
       iout_file++;
     }
   };
@@ -352,6 +360,7 @@ int main(int argc, char** argv)
   double tout = t0 + dTout;
   for (int iout = 0; iout < nout; iout++) {
     if (S.evolve(tout) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
+    outputs_done++;
     fetch();
     diagnostics(S.t);
     stats(S.t, 1);

@@ -159,3 +159,30 @@ def test_initial_transient_then_fixed_steps_equals_the_python_driver(pkg, port, 
     sol = pkg.problems.read_solution(str(tmp_path / pkg.problems.solution_name(1)))
     for f, name in enumerate(pkg.problems.dataset_names(0)):
         assert np.abs(sol[name].ravel() - step.w.sub[f]).max() <= 1e-12 * max(np.abs(step.w.sub[f]).max(), 1.0), name
+
+
+def test_restart_parameters_file_continues_the_run(pkg, exe, tmp_path):
+    """write_parameters (io.cpp:645-714): every solution file comes with a restart_parameters.txt that
+    continues the run (`-f restart_parameters.txt`): t0 = the file's time, the remaining outputs, the
+    current step, restart = <file number>.  Half a run plus its continuation ends where the whole run ends."""
+    base = ["--problem=linear_advection_x", "--nx=24", "--ny=3", "--nz=3", "--fixedstep=1", "--hmax=0.005", "--output=1"]
+    whole = tmp_path / "whole"
+    halves = tmp_path / "halves"
+    whole.mkdir(), halves.mkdir()
+    run(exe, base + ["--tf=0.1", "--nout=2"], whole)
+    run(exe, base + ["--tf=0.1", "--nout=2", "--mxsteps=5000"], halves)      # same run ...
+    par = (halves / "restart_parameters.txt").read_text()
+    assert "problem = linear_advection_x" in par and re.search(r"^restart = 2$", par, re.M) and re.search(r"^nout = 0$", par, re.M)
+    # ... and one that stops after the first output interval, then continues from its parameter file
+    for f in halves.iterdir():
+        f.unlink()
+    run(exe, base + ["--tf=0.05", "--nout=1"], halves)
+    par = (halves / "restart_parameters.txt").read_text()
+    assert re.search(r"^restart = 1$", par, re.M) and re.search(r"^t0 = 0\.05", par, re.M)
+    out = run(exe, ["-f", "restart_parameters.txt", "--tf=0.1", "--nout=1"], halves)
+    assert "restarting from output-0000001.eb200 at t = 0.05" in out
+    a = pkg.problems.read_solution(str(whole / pkg.problems.solution_name(2)))
+    b = pkg.problems.read_solution(str(halves / pkg.problems.solution_name(2)))
+    assert a["time"] == b["time"] == 0.1
+    for name in pkg.problems.dataset_names(0):
+        assert np.abs(a[name] - b[name]).max() <= 1e-13 * max(np.abs(a[name]).max(), 1e-300), name
