@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -36,6 +37,18 @@
 namespace {
 
 using eb_problems::Problem;
+
+// Cumulative wall-clock timers of the run regions the reference profiles (class Profile,
+// profiler.hpp:50-108; slots of euler3D.hpp:97-118 that exist here).  The RHS and stability calls of
+// this driver return after the device has finished, so host timers around them are meaningful.
+struct Timer {
+  double total = 0, t0 = -1;
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  void start() { t0 = now(); }
+  void stop() { if (t0 >= 0) total += now() - t0; t0 = -1; }
+  void print(const char* name) const { printf("Total %s time = \t%.2e  ( min / max  =  %.2e / %.2e )\n", name, total, total, total); }
+};
+Timer g_prof_rhs, g_prof_stab;
 
 struct Inputs {
   std::map<std::string, double> v;
@@ -104,12 +117,16 @@ struct DeviceOps {
   }
   int rhs(double tt, Vec& y, Vec& out)
   {
+    g_prof_rhs.start();
     if (eulerb200_rhs(ctx, tt, y.sub, out.sub, NULL)) die("fEuler");
+    g_prof_rhs.stop();
     return 0;
   }
   int stability(Vec& w, double, double cfl, double* dt)
   {
+    g_prof_stab.start();
     if (eulerb200_stability(ctx, w.sub, cfl, dt, NULL)) die("stability");
+    g_prof_stab.stop();
     return 0;
   }
 };
@@ -137,6 +154,8 @@ static void usage()
 
 int main(int argc, char** argv)
 {
+  Timer prof_setup, prof_io, prof_trans, prof_sim;
+  prof_setup.start();
   Inputs in;
   std::vector<std::string> overrides;
   for (int a = 1; a < argc; a++) {
@@ -345,35 +364,47 @@ int main(int argc, char** argv)
     }
   };
 
+  prof_io.start();
   printf("\nWriting initial batch of outputs\n");
   if (showstats) conservation();
   fetch();
   write_file(t0);
   stats(t0, 0);
   diagnostics(t0);
+  prof_io.stop();
+  prof_setup.stop();
 
   if (fixed_mode == 2) {               // initial transient (euler3D_main.cpp:340-367)
+    prof_trans.start();
     if (S.evolve(t0 + htrans) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
     S.fixedstep = 1; S.h = 0.0;         // ARKStepSetFixedStep(hmax)
+    prof_trans.stop();
   }
+  prof_sim.start();
   const double dTout = (tf - t0) / nout;
   double tout = t0 + dTout;
   for (int iout = 0; iout < nout; iout++) {
     if (S.evolve(tout) != 0) { fprintf(stderr, "Solver failure, stopping integration\n"); return 1; }
     outputs_done++;
+    prof_io.start();
     fetch();
     diagnostics(S.t);
     stats(S.t, 1);
     write_file(S.t);
+    prof_io.stop();
     tout = std::min(tout + dTout, tf);
   }
   stats(S.t, 2);
+  prof_sim.stop();
 
   printf("\nFinal Solver Statistics:\n");
   printf("   Internal solver steps = %ld (attempted = %ld)\n", S.nst, S.nst_a);
   printf("   Total RHS evals:  Fe = %ld,  Fi = 0\n", S.nfe);
   printf("   Total number of error test failures = %ld\n", S.netf);
   printf("   GPU kernel launches = %lld\n", (long long)eulerb200_launch_count(ctx));
+  printf("\nProfiling Results:\n");                         // euler3D_main.cpp:449-461 (the slots that exist here)
+  prof_setup.print("setup"); prof_io.print("I/O"); g_prof_rhs.print("RHS"); g_prof_stab.print("dt_stab");
+  prof_trans.print("trans"); prof_sim.print("sim");
   if (showstats) { printf("\nConservation Check:\n"); conservation(); }
 
   free_vec(S.w); free_vec(S.ytmp); free_vec(S.yerr);
