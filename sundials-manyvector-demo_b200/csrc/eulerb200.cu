@@ -3,8 +3,8 @@
 //
 // Kernels in this translation unit:
 //   rhs_fused_kernel     (rhs_kernel.cuh)  fEuler: faces + divergence, one pass
-//   pack_face_kernel     halo pack of EulerData::ExchangeStart (euler3D.hpp:644-786)
-//   ghost_face_kernel    materialise a face's ghost layers in the reference's
+//   pack_face_kernel     (halo_kernels.cuh) halo pack of EulerData::ExchangeStart (euler3D.hpp:644-786)
+//   ghost_face_kernel    (halo_kernels.cuh) materialise a face's ghost layers in the reference's
 //                        receive-buffer layout (euler3D.hpp:797-1166; tests, drop-in)
 //   wavespeed_kernel     local part of stability (utilities.cpp:505-513)
 // There is deliberately no host implementation of any of them.
@@ -21,6 +21,7 @@
 
 #define EB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #include "host_setup.h"
+#include "halo_kernels.cuh"
 
 namespace {
 
@@ -71,75 +72,6 @@ NcclApi& nccl()
 }
 
 // ----------------------------------- small kernels -----------------------------------
-
-struct FaceGeom {
-  long nx, ny, nz;
-  int nchem, f;
-  const double* w[6];
-};
-
-__device__ __forceinline__ void face_decode(const FaceGeom& g, long e, int& d, long& a, long& b, long& na)
-{
-  const int dir = g.f / 2;
-  na = (dir == 0) ? g.ny : g.nx;
-  d = (int)(e % 3);
-  const long r = e / 3;
-  a = r % na;
-  b = r / na;
-}
-__device__ __forceinline__ long face_cell(const FaceGeom& g, long src, long a, long b)
-{
-  const int dir = g.f / 2;
-  const long i = (dir == 0) ? src : a;
-  const long j = (dir == 0) ? a : (dir == 1 ? src : b);
-  const long k = (dir == 2) ? src : b;
-  return i + g.nx * (j + g.ny * k);
-}
-
-// What this rank sends through face f: its three layers nearest that face in increasing
-// index order, all NVAR values of a cell contiguous (euler3D.hpp:644-786).
-__global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
-{
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
-  int d; long a, b, na;
-  face_decode(g, e, d, a, b, na);
-  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
-  const long src = (g.f % 2 == 0) ? d : n - 3 + d;
-  const long cell = face_cell(g, src, a, b);
-  const int nv = 5 + g.nchem;
-  double* o = buf + (long)nv * e;
-#pragma unroll
-  for (int v = 0; v < 5; v++) o[v] = g.w[v][cell];
-  for (int v = 0; v < g.nchem; v++) o[5 + v] = g.w[5][cell * g.nchem + v];
-  }
-}
-
-// Ghost layers of face f in the reference's receive-buffer layout, from the descriptor
-// the RHS kernel itself uses (so tests of this buffer test the kernel's ghost semantics).
-__global__ void ghost_face_kernel(const FaceGeom g, const eb::GhostFace G, double* __restrict__ dst, long nent)
-{
-  const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (e >= nent) return;
-  const int nv = 5 + g.nchem;
-  double* o = dst + (long)nv * e;
-  if (G.mode == eb::GHOST_BUF) {
-    for (int v = 0; v < nv; v++) o[v] = G.buf[(long)nv * e + v];
-    return;
-  }
-  int d; long a, b, na;
-  face_decode(g, e, d, a, b, na);
-  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
-  const long pos = (g.f % 2 == 0) ? (long)d - 3 : n + d;
-  const long cell = face_cell(g, G.a + (long)G.b * pos, a, b);
-  for (int v = 0; v < 5; v++) {
-    const double x = g.w[v][cell];
-    o[v] = ((G.neg >> v) & 1u) ? -x : x;
-  }
-  for (int v = 0; v < g.nchem; v++) {
-    const double x = g.w[5][cell * g.nchem + v];
-    o[5 + v] = ((G.neg >> 5) & 1u) ? -x : x;
-  }
-}
 
 // utilities.cpp:505-513: alpha = max | |mx/rho| + sqrt(gamma p / rho) |  (my, mz only via p).
 // Warp-shuffle then one atomic per CTA; non-negative doubles order like their bit patterns.
@@ -423,9 +355,9 @@ int launch_aux(eulerb200_ctx* c, const eb::RhsParams& P, long k0, long k1, cudaS
   return 0;
 }
 
-FaceGeom face_geom(const eulerb200_ctx* c, int f, const double* const* w)
+eb::FaceGeom face_geom(const eulerb200_ctx* c, int f, const double* const* w)
 {
-  FaceGeom g;
+  eb::FaceGeom g;
   g.nx = c->cfg.nxl; g.ny = c->cfg.nyl; g.nz = c->cfg.nzl;
   g.nchem = c->cfg.nchem; g.f = f;
   for (int q = 0; q < 6; q++) g.w[q] = (q < 5 || c->cfg.nchem > 0) ? w[q] : nullptr;
@@ -449,7 +381,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
       if (!c->remote[f]) continue;
       const long nent = eb::face_len(c->cfg, f) / nv;
       double* dst = reinterpret_cast<double*>(c->peer_base[f] + c->peer_slab_off[f][par]);
-      pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
+      eb::pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
       halo_signal_kernel<<<1, 1, 0, c->comm_stream>>>(
           reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
       c->launches += 2;
@@ -464,7 +396,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
   for (int f = 0; f < 6; f++) {
     if (!c->remote[f]) continue;
     const long nent = eb::face_len(c->cfg, f) / nv;
-    pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), c->send[f], nent);
+    eb::pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), c->send[f], nent);
     c->launches++;
   }
   EB_CUDA(c, cudaGetLastError());
@@ -777,7 +709,7 @@ int eulerb200_ghost_face(eulerb200_ctx* c, const double* const* w, int32_t f, do
   eb::GhostFace G;
   eb::ghost_face(c->cfg, f, c->recv_cur[f], &G);
   const long nent = eb::face_len(c->cfg, f) / (5 + c->cfg.nchem);
-  ghost_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, (cudaStream_t)stream>>>(face_geom(c, f, w), G, dst, nent);
+  eb::ghost_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, (cudaStream_t)stream>>>(face_geom(c, f, w), G, dst, nent);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;

@@ -117,6 +117,25 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
         }
       }
 }
+// Kernels without barriers or shared memory (grid-stride loops): every thread runs to completion in turn.
+template <class K, class... A>
+void launch_plain(K kernel, dim3 grid, dim3 block, A... args)
+{
+  gdim() = grid; bdim() = block;
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        bidx().x = bx; bidx().y = by; bidx().z = bz;
+        for (unsigned tz = 0; tz < block.z; tz++)
+          for (unsigned ty = 0; ty < block.y; ty++)
+            for (unsigned tx = 0; tx < block.x; tx++) {
+              tidx().x = tx; tidx().y = ty; tidx().z = tz;
+              kernel(args...);
+            }
+      }
+}
+template <class K, class A, class B, class C> void launch2(K k, dim3 g, dim3 b, A a0, B a1, C a2) { launch_plain(k, g, b, a0, a1, a2); }
+template <class K, class A, class B, class C, class D> void launch3(K k, dim3 g, dim3 b, A a0, B a1, C a2, D a3) { launch_plain(k, g, b, a0, a1, a2, a3); }
 // grid-stride "for each cell" helper for trivially parallel pre-pass kernels
 template <class F> void launch_aux_like(F f, long n) { for (long c = 0; c < n; c++) f(c); }
 }  // namespace cuda_emu

@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 
 def build():
     deps = [os.path.join(HERE, f) for f in ("emu_rhs.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "euler_math.cuh", "host_setup.h")]
+           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "halo_kernels.cuh", "euler_math.cuh", "host_setup.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-ffp-contract=off",
                                "-o", SO, os.path.join(HERE, "emu_rhs.cpp")])
@@ -35,6 +35,28 @@ class Emu:
         self.pkg = pkg
         self.lib = C.CDLL(build())
         self.lib.emu_rhs.restype = C.c_int
+
+    def _config(self, n, nchem, d, gamma, bcs, nbr, rank):
+        c = self.pkg.Config()
+        c.nxl, c.nyl, c.nzl = n
+        c.nchem, c.device = nchem, -1
+        c.dx, c.dy, c.dz, c.gamma = d[0], d[1], d[2], gamma
+        for f in range(6):
+            c.bc[f], c.nbr[f] = bcs[f], nbr[f]
+        c.rank, c.nranks = rank, 1
+        return c
+
+    def face(self, what, n, nchem, bcs, nbr, rank, w, f, recv=None):
+        """what = 'pack': the send buffer of face f (pack_face_kernel); 'ghost': the ghost layers of
+        face f in the reference's receive-buffer layout (ghost_face_kernel)."""
+        c = self._config(n, nchem, (1.0, 1.0, 1.0), 1.4, bcs, nbr, rank)
+        other = (n[1] * n[2], n[0] * n[2], n[0] * n[1])[f // 2]
+        out = np.full((5 + nchem) * 3 * other, np.nan)
+        self.lib.emu_face.restype = C.c_int
+        ret = self.lib.emu_face(C.byref(c), _ptrs(w), _ptrs(recv) if recv is not None else None, f,
+                                0 if what == "pack" else 1, out.ctypes.data_as(_dp))
+        assert ret == 0
+        return out
 
     def rhs(self, n, nchem, d, gamma, bcs, nbr, rank, w, forcing=None, recv=None, lo=None, hi=None, threads=256,
             use_aux=1, energy_units=0.0, pair=0, g_in_wdot=None, aux_in_gen=0):

@@ -5,6 +5,7 @@
 // ---------------------------------------------------------------------------
 #include "cuda_emu.h"
 #include "../../sundials-manyvector-demo_b200/csrc/host_setup.h"
+#include "../../sundials-manyvector-demo_b200/csrc/halo_kernels.cuh"
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
@@ -66,4 +67,26 @@ extern "C" double emu_boundary_tile_fraction(const long* lo, const long* hi, lon
 {
   const eb::LaunchGeom L = eb::launch_geom(lo, hi, nchem, threads, 2);
   return eb::boundary_tile_fraction(lo, hi, nx, ny, L);
+}
+
+// The face kernels of the halo exchange (halo_kernels.cuh), launched like exchange_start() /
+// eulerb200_ghost_face() launch them.  what = 0: pack the send buffer of face f; 1: the ghost layers
+// of face f (recv: this rank's halo slabs, NULL where a face has no remote neighbour).
+extern "C" int emu_face(const eulerb200_config* cfg, const double* const* w, const double* const* recv, int f, int what,
+                        double* out)
+{
+  eb::FaceGeom g;
+  g.nx = cfg->nxl; g.ny = cfg->nyl; g.nz = cfg->nzl;
+  g.nchem = cfg->nchem; g.f = f;
+  for (int q = 0; q < 6; q++) g.w[q] = (q < 5 || cfg->nchem > 0) ? w[q] : nullptr;
+  const long nent = eb::face_len(*cfg, f) / (5 + cfg->nchem);
+  const dim3 grid((unsigned)((nent + 255) / 256)), block(256);
+  if (what == 0) {
+    cuda_emu::launch2(eb::pack_face_kernel, grid, block, g, out, nent);
+  } else {
+    eb::GhostFace G;
+    if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &G) != 0) return -1;
+    cuda_emu::launch3(eb::ghost_face_kernel, grid, block, g, G, out, nent);
+  }
+  return 0;
 }

@@ -247,8 +247,8 @@ def test_emulated_random_configurations(emu, oracle_mod, port):
 def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
     """Seeded sweep of the N>1 kernel path without GPUs: 60 random grids / BC mixes split over 2, 4
     or 8 ranks the way SetupDecomp does (splits along every axis, periodic wraps onto other ranks),
-    every rank reading its neighbours' packed layers (wire layout of euler3D.hpp:648,696,744) as
-    halo buffers and evaluating interior box and the six boundary slabs as separate sub-box launches
+    every rank reading the layers its neighbours' pack_face_kernel produced (wire layout of
+    euler3D.hpp:648,696,744) as halo buffers and evaluating interior box and the six boundary slabs as separate sub-box launches
     exactly like eulerb200_rhs_async; the assembled result against the single-rank oracle on the
     global grid (the decomposed result is the single-rank result)."""
     rng = np.random.default_rng(8)
@@ -281,8 +281,8 @@ def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
             recv = [None] * 6
             for f in range(6):
                 o = b["nbr"][f]
-                if o not in (NO, rank):
-                    recv[f] = port.pack_send(port.cfg(blocks[o]["nl"], nchem, d, 1.4, bcs), blocks[o]["parts"], f ^ 1)
+                if o not in (NO, rank):            # what the neighbour's pack_face_kernel sends through its opposite face
+                    recv[f] = emu.face("pack", blocks[o]["nl"], nchem, bcs, blocks[o]["nbr"], o, blocks[o]["parts"], f ^ 1)
             nl = b["nl"]
             Nl = nl[0] * nl[1] * nl[2]
             out = [np.full(Nl, np.nan) for _ in range(5)] + ([np.full(Nl * nchem, np.nan)] if nchem else [])
@@ -308,3 +308,27 @@ def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
             want = [np.ascontiguousarray(a[b["sl"]]).ravel() for a in R3]
             assert not any(np.isnan(o_).any() for o_ in out), tag
             assert max(normwise_errors(out, want)) <= 1e-12, tag
+
+
+@pytest.mark.parametrize("n,nchem", [((12, 10, 8), 2), ((3, 9, 7), 0), ((5, 3, 4), 4)])
+def test_emulated_pack_and_ghost_face_kernels_exact(emu, oracle_mod, port, n, nchem):
+    """halo_kernels.cuh on the CPU tier, exact (they only move values): pack_face_kernel against the
+    oracle's restatement of ExchangeStart's send buffers (euler3D.hpp:644-786) for all six faces, and
+    ghost_face_kernel against its boundary-condition fills (euler3D.hpp:797-1166) for every BC type
+    and against a halo slab handed in as receive buffer."""
+    w = oracle_mod.random_state(n, nchem, seed=31)
+    d = (1.0, 1.0, 1.0)
+    for bcs in ([P] * 6, [N] * 6, [R] * 6, [D] * 6, [N, N, R, R, P, P], [R, R, D, D, N, N]):
+        cfg = port.cfg(n, nchem, d, 1.4, bcs)
+        for f in range(6):
+            assert np.array_equal(emu.face("pack", n, nchem, bcs, nbr_single(bcs), 0, w, f), port.pack_send(cfg, w, f))
+            got = emu.face("ghost", n, nchem, bcs, nbr_single(bcs), 0, w, f)
+            if bcs[f] == P:      # single rank: the periodic ghost layers are the opposite side's send layers
+                assert np.array_equal(got, port.pack_send(cfg, w, f ^ 1))
+            else:
+                assert np.array_equal(got, port.fill_ghost(cfg, w, f))
+    # a remote neighbour: the ghost layers are whatever the halo slab holds
+    slab = np.arange((5 + nchem) * 3 * n[1] * n[2], dtype=np.float64)
+    nbr = [1, NO, NO, NO, NO, NO]
+    got = emu.face("ghost", n, nchem, [N] * 6, nbr, 0, w, 0, recv=[slab, None, None, None, None, None])
+    assert np.array_equal(got, slab)
