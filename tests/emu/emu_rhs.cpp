@@ -23,23 +23,19 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
   for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
   P.slow_mode = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
-  if (energy_units > 0.0) {        // fslow mode: the energy rebuild that aux_kernel does on the device
+  if (energy_units > 0.0) {        // fslow mode: aux_kernel rebuilds the total energy in w[4]
     P.slow_mode = 1;
     P.inv_energy_units = 1.0 / energy_units;
     P.et_rw = const_cast<double*>(w[4]);
-    const long N = P.nx * P.ny * P.nz;
-    for (long c = 0; c < N; c++)
-      P.et_rw[c] = w[5][c * P.nchem + (P.nchem - 1)] * P.inv_energy_units
-                   + 0.5 / w[0][c] * (w[1][c] * w[1][c] + w[2][c] * w[2][c] + w[3][c] * w[3][c]);
   }
-  if (use_aux) {
+  if (use_aux || P.slow_mode) {    // the product's own pre-pass kernel, launched like launch_aux() launches it
     const long N = P.nx * P.ny * P.nz;
-    for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);
-    cuda_emu::launch_aux_like([&](long c) {
-      const eb::CellAux a = eb::cell_aux(P.gamma, w[0][c], w[1][c], w[2][c], w[3][c], w[4][c]);
-      aux[0][c] = a.rinv; aux[1][c] = a.p; aux[2][c] = a.c; aux[3][c] = a.sr;
-    }, N);
-    for (int q = 0; q < 4; q++) P.aux[q] = aux[q].data();
+    if (use_aux) for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);
+    double* a[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (use_aux) for (int q = 0; q < 4; q++) a[q] = aux[q].data();
+    cuda_emu::launch_plain(eb::aux_kernel, dim3((unsigned)std::min<long>((N + 255) / 256, 148L * 16)), dim3(256), P,
+                           a[0], a[1], a[2], a[3], 0L, N);
+    if (use_aux) for (int q = 0; q < 4; q++) P.aux[q] = aux[q].data();
   }
   int flag = 0;
   P.state_flag = &flag;
