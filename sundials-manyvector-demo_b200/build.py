@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeulerb200.so")
 SOURCES = ["eulerb200.cu"]
-HEADERS = ["rhs_kernel.cuh", "halo_kernels.cuh", "euler_math.cuh", "host_setup.h", os.path.join("..", "..", "include", "eulerb200.h")]
+HEADERS = ["rhs_kernel.cuh", "halo_kernels.cuh", "vector_kernels.cuh", "euler_math.cuh", "host_setup.h", os.path.join("..", "..", "include", "eulerb200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -6,7 +6,8 @@
 //   pack_face_kernel     (halo_kernels.cuh) halo pack of EulerData::ExchangeStart (euler3D.hpp:644-786)
 //   ghost_face_kernel    (halo_kernels.cuh) materialise a face's ghost layers in the reference's
 //                        receive-buffer layout (euler3D.hpp:797-1166; tests, drop-in)
-//   wavespeed_kernel     local part of stability (utilities.cpp:505-513)
+//   wavespeed_kernel     (vector_kernels.cuh) local part of stability (utilities.cpp:505-513)
+//   lincomb_kernel, wrms_kernel (vector_kernels.cuh) vector operations of the explicit driver loop
 // There is deliberately no host implementation of any of them.
 // ---------------------------------------------------------------------------
 #include <cuda_runtime.h>
@@ -22,6 +23,7 @@
 #define EB_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #include "host_setup.h"
 #include "halo_kernels.cuh"
+#include "vector_kernels.cuh"
 
 namespace {
 
@@ -73,41 +75,6 @@ NcclApi& nccl()
 
 // ----------------------------------- small kernels -----------------------------------
 
-// utilities.cpp:505-513: alpha = max | |mx/rho| + sqrt(gamma p / rho) |  (my, mz only via p).
-// Warp-shuffle then one atomic per CTA; non-negative doubles order like their bit patterns.
-__global__ void wavespeed_kernel(const double* __restrict__ rho, const double* __restrict__ mx,
-                                 const double* __restrict__ my, const double* __restrict__ mz,
-                                 const double* __restrict__ et, long N, double gamma,
-                                 unsigned long long* __restrict__ out)
-{
-  double alpha = 0.0;
-  for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < N; c += (long)gridDim.x * blockDim.x) {
-    const double r = rho[c], a = mx[c], b = my[c], d = mz[c];
-    const double u = fabs(a / r);
-    const double p = (gamma - 1.0) * (et[c] - (a * a + b * b + d * d) * 0.5 / r);
-    const double x = fabs(u + eb::sun_sqrt(gamma * p / r));
-    alpha = (alpha < x) ? x : alpha;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double y = __shfl_xor_sync(0xffffffffu, alpha, o);
-    alpha = (alpha < y) ? y : alpha;
-  }
-  __shared__ double part[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) part[wid] = alpha;
-  __syncthreads();
-  if (wid == 0) {
-    alpha = (lane < (blockDim.x >> 5)) ? part[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double y = __shfl_xor_sync(0xffffffffu, alpha, o);
-      alpha = (alpha < y) ? y : alpha;
-    }
-    if (lane == 0) atomicMax(out, (unsigned long long)__double_as_longlong(alpha));
-  }
-}
-
 // ---- peer-store halo exchange (transport (b)): the pack kernel writes the
 // three layers straight into the NEIGHBOUR's ghost slab over NVLink (CUDA IPC mapping of the
 // neighbour's mailbox); a release store of the exchange's sequence number into the neighbour's
@@ -131,47 +98,6 @@ __global__ void halo_wait_kernel(const unsigned long long* arrival, unsigned mas
       if (clock64() - t0 > timeout_cycles) { atomicOr(err, 8); break; }
       __nanosleep(200);
     } while (true);
-  }
-}
-
-// ---- vector operations of the explicit driver loop: the stage
-// combinations and the weighted RMS norm ARKODE evaluates through N_VLinearCombination /
-// N_VWrmsNorm on the MPIManyVector.  One pass each, HBM bound, grid-stride over a grid that
-// is a multiple of the SM count.
-struct LinCombArgs {
-  int nterms;
-  double c[8];
-  const double* x[8];
-};
-__global__ void lincomb_kernel(const LinCombArgs a, double* __restrict__ out, long n)
-{
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    double s = a.c[0] * a.x[0][i];
-#pragma unroll 1
-    for (int t = 1; t < a.nterms; t++) s = fma(a.c[t], a.x[t][i], s);
-    out[i] = s;
-  }
-}
-// sum_i (x_i / (rtol*|y_i| + atol))^2  accumulated into *acc (one atomicAdd per CTA)
-__global__ void wrms_kernel(const double* __restrict__ x, const double* __restrict__ y, double rtol, double atol,
-                            long n, double* __restrict__ acc)
-{
-  double s = 0.0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const double q = x[i] / fma(rtol, fabs(y[i]), atol);
-    s = fma(q, q, s);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  __shared__ double part[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) part[wid] = s;
-  __syncthreads();
-  if (wid == 0) {
-    s = (lane < (blockDim.x >> 5)) ? part[lane] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) atomicAdd(acc, s);
   }
 }
 
@@ -937,7 +863,7 @@ int eulerb200_stability(eulerb200_ctx* c, const double* const* w, double cfl, do
   const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
   EB_CUDA(c, cudaMemsetAsync(c->d_alpha, 0, sizeof(unsigned long long), s));
   const unsigned blocks = (unsigned)std::min<long>((N + 255) / 256, 148L * 8);
-  wavespeed_kernel<<<blocks, 256, 0, s>>>(w[0], w[1], w[2], w[3], w[4], N, c->cfg.gamma, c->d_alpha);
+  eb::wavespeed_kernel<<<blocks, 256, 0, s>>>(w[0], w[1], w[2], w[3], w[4], N, c->cfg.gamma, c->d_alpha);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   if (c->cfg.nranks > 1 && c->comm)   // utilities.cpp:516
@@ -969,11 +895,11 @@ int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, 
                           double* out, int64_t n, void* stream)
 {
   if (!c || !coef || !x || !out || nterms < 1 || nterms > 8) return -1;
-  LinCombArgs a;
+  eb::LinCombArgs a;
   a.nterms = nterms;
   for (int t = 0; t < nterms; t++) { a.c[t] = coef[t]; a.x[t] = x[t]; }
   const unsigned blocks = (unsigned)std::min<long>((n + 255) / 256, 148L * 16);
-  lincomb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out, n);
+  eb::lincomb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out, n);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
@@ -984,7 +910,7 @@ int eulerb200_vec_wrms_accum(eulerb200_ctx* c, const double* x, const double* y,
 {
   if (!c || !x || !y || !acc) return -1;
   const unsigned blocks = (unsigned)std::min<long>((n + 255) / 256, 148L * 8);
-  wrms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, rtol, atol, n, acc);
+  eb::wrms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, rtol, atol, n, acc);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;

@@ -28,6 +28,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __shared__ static            /* one CTA runs at a time */
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3_emu { unsigned x, y, z; };
@@ -80,7 +81,8 @@ void launch(void (*kernel)(const Params), dim3 grid, dim3 block, size_t shmem, c
   gdim() = grid; bdim() = block;
   const int T = block.x * block.y * block.z;
   std::vector<char> smem(shmem + 64);
-  std::vector<std::vector<char> > stacks(T, std::vector<char>(96 * 1024));   // reused by every CTA
+  static std::vector<std::vector<char> > stacks;                             // reused by every CTA and launch
+  while ((int)stacks.size() < T) stacks.push_back(std::vector<char>(96 * 1024));
   for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -155,3 +157,24 @@ inline void __syncwarp()
   cuda_emu::barrier_wait(16 + w, (T - 32 * w < 32) ? T - 32 * w : 32);
 }
 inline int atomicOr(int* addr, int v) { int old = *addr; *addr = old | v; return old; }
+inline double atomicAdd(double* addr, double v) { const double old = *addr; *addr = old + v; return old; }
+inline unsigned long long atomicMax(unsigned long long* addr, unsigned long long v)
+{
+  const unsigned long long old = *addr;
+  if (v > old) *addr = v;
+  return old;
+}
+inline long long __double_as_longlong(double x) { long long y; memcpy(&y, &x, sizeof y); return y; }
+// Full-warp butterfly exchange: every lane of the (complete) warp deposits its value, meets the others
+// at the warp barrier, reads its partner's, and meets them again before the slot is reused.
+inline double __shfl_xor_sync(unsigned, double v, int lane_mask)
+{
+  static std::vector<double> slot;
+  const int t = cuda_emu::current(), T = emu_block_threads();
+  if ((int)slot.size() < T) slot.resize(T);
+  slot[t] = v;
+  __syncwarp();
+  const double r = slot[(t & ~31) | ((t & 31) ^ lane_mask)];
+  __syncwarp();
+  return r;
+}

@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 
 def build():
     deps = [os.path.join(HERE, f) for f in ("emu_rhs.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "halo_kernels.cuh", "euler_math.cuh", "host_setup.h")]
+           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "halo_kernels.cuh", "vector_kernels.cuh", "euler_math.cuh", "host_setup.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-ffp-contract=off",
                                "-o", SO, os.path.join(HERE, "emu_rhs.cpp")])

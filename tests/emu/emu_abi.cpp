@@ -19,6 +19,10 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
                        int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen);
 
+extern "C" double emu_max_wavespeed(const double* const* w, long N, double gamma);
+extern "C" void emu_lincomb(int nterms, const double* coef, const double* const* x, double* out, long n);
+extern "C" void emu_wrms_accum(const double* x, const double* y, double rtol, double atol, long n, double* acc);
+
 struct eulerb200_ctx { eulerb200_config cfg; bool gw; std::string err; long launches; };
 static std::string g_err;
 
@@ -42,17 +46,9 @@ int eulerb200_rhs_any(eulerb200_ctx* c, double, const double* const* w, double* 
 }
 int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl, double* dt_stab, void*)
 {
-  // utilities.cpp:505-520, same expression as wavespeed_kernel
+  // utilities.cpp:505-520 through the product's wavespeed_kernel
   const long N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
-  const double g = c->cfg.gamma;
-  double alpha = 0.0;
-  for (long i = 0; i < N; i++) {
-    const double r = w[0][i], a = w[1][i], b = w[2][i], d = w[3][i];
-    const double p = (g - 1.0) * (w[4][i] - (a * a + b * b + d * d) * 0.5 / r);
-    const double s = g * p / r;
-    const double x = std::fabs(std::fabs(a / r) + (s <= 0.0 ? 0.0 : std::sqrt(s)));
-    alpha = alpha < x ? x : alpha;
-  }
+  const double alpha = emu_max_wavespeed(w, N, c->cfg.gamma);
   *dt_stab = cfl * std::fmin(std::fmin(c->cfg.dx, c->cfg.dy), c->cfg.dz) / alpha;
   return 0;
 }
@@ -71,16 +67,12 @@ void eulerb200_device_free(void* p) { free(p); }
 int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
 int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
-// lincomb_kernel / wrms_kernel of eulerb200.cu, same expressions (the sum order of the norm differs)
+// the product's lincomb_kernel / wrms_kernel (vector_kernels.cuh) through the emulator
 int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x, double* out,
                           int64_t n, void*)
 {
   if (!c || nterms < 1 || nterms > 8) return -1;
-  for (int64_t i = 0; i < n; i++) {
-    double s = coef[0] * x[0][i];
-    for (int t = 1; t < nterms; t++) s = std::fma(coef[t], x[t][i], s);
-    out[i] = s;
-  }
+  emu_lincomb(nterms, coef, x, out, (long)n);
   c->launches++;
   return 0;
 }
@@ -90,11 +82,7 @@ int eulerb200_vec_wrms(eulerb200_ctx* c, const double* const* x, const double* c
   const int64_t N = c->cfg.nxl * c->cfg.nyl * c->cfg.nzl;
   double acc = 0.0;
   for (int f = 0; f < 5 + (c->cfg.nchem > 0 ? 1 : 0); f++) {
-    const int64_t len = f < 5 ? N : N * c->cfg.nchem;
-    for (int64_t i = 0; i < len; i++) {
-      const double q = x[f][i] / std::fma(rtol, std::fabs(y[f][i]), atol);
-      acc = std::fma(q, q, acc);
-    }
+    emu_wrms_accum(x[f], y[f], rtol, atol, (long)(f < 5 ? N : N * c->cfg.nchem), &acc);
     c->launches++;
   }
   *result = std::sqrt(acc / (double)nglobal);

@@ -6,6 +6,7 @@
 #include "cuda_emu.h"
 #include "../../sundials-manyvector-demo_b200/csrc/host_setup.h"
 #include "../../sundials-manyvector-demo_b200/csrc/halo_kernels.cuh"
+#include "../../sundials-manyvector-demo_b200/csrc/vector_kernels.cuh"
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
@@ -85,4 +86,43 @@ extern "C" int emu_face(const eulerb200_config* cfg, const double* const* w, con
     cuda_emu::launch3(eb::ghost_face_kernel, grid, block, g, G, out, nent);
   }
   return 0;
+}
+
+// The reduction / vector kernels (vector_kernels.cuh), launched like the C ABI launches them.  They
+// use barriers and warp shuffles, so they go through the fibre scheduler (one parameter struct each).
+namespace {
+struct WaveArgs { const double* w[5]; long N; double gamma; unsigned long long* out; };
+void wave_entry(const WaveArgs a) { eb::wavespeed_kernel(a.w[0], a.w[1], a.w[2], a.w[3], a.w[4], a.N, a.gamma, a.out); }
+struct LinArgs { eb::LinCombArgs a; double* out; long n; };
+void lin_entry(const LinArgs a) { eb::lincomb_kernel(a.a, a.out, a.n); }
+struct WrmsArgs { const double* x; const double* y; double rtol, atol; long n; double* acc; };
+void wrms_entry(const WrmsArgs a) { eb::wrms_kernel(a.x, a.y, a.rtol, a.atol, a.n, a.acc); }
+// (two warps per CTA and at most three CTAs: enough to exercise the warp, CTA and grid levels of the
+// reductions while keeping the fibre count per launch small)
+unsigned emu_blocks(long n) { return n <= 512 ? 1u : (n <= 4096 ? 2u : 3u); }
+}  // namespace
+
+extern "C" double emu_max_wavespeed(const double* const* w, long N, double gamma)
+{
+  unsigned long long bits = 0;
+  WaveArgs a;
+  for (int f = 0; f < 5; f++) a.w[f] = w[f];
+  a.N = N; a.gamma = gamma; a.out = &bits;
+  cuda_emu::launch(wave_entry, dim3(emu_blocks(N)), dim3(64), 0, a);
+  double alpha;
+  memcpy(&alpha, &bits, sizeof alpha);
+  return alpha;
+}
+extern "C" void emu_lincomb(int nterms, const double* coef, const double* const* x, double* out, long n)
+{
+  LinArgs a;
+  a.a.nterms = nterms;
+  for (int t = 0; t < nterms; t++) { a.a.c[t] = coef[t]; a.a.x[t] = x[t]; }
+  a.out = out; a.n = n;
+  cuda_emu::launch_plain(lin_entry, dim3(emu_blocks(n)), dim3(64), a);      // no barriers or shuffles: no fibres needed
+}
+extern "C" void emu_wrms_accum(const double* x, const double* y, double rtol, double atol, long n, double* acc)
+{
+  WrmsArgs a = {x, y, rtol, atol, n, acc};
+  cuda_emu::launch(wrms_entry, dim3(emu_blocks(n)), dim3(64), 0, a);
 }
