@@ -160,6 +160,7 @@ struct eulerb200_ctx {
   bool host_ready = false;
   size_t max_smem_set[3] = {0, 0, 0}, carveout_for[3] = {(size_t)-1, (size_t)-1, (size_t)-1};   // per kernel instantiation
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
+  long ctas_target = 5920;       // EULERB200_CTAS: CTAs a launch aims for when cutting z-segments (tuning)
   int force_kernel = 0;          // EULERB200_KERNEL=1: allow the AG instantiation for boundary-heavy launches
   int variant = 0;
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
@@ -242,7 +243,7 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
   const KernelVariant& V = kVariants[c->variant];
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync);
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync, c->ctas_target);
   // which instantiation: hook-assigned forcing -> [2]; with EULERB200_KERNEL=1 a launch in which a
   // quarter or more of the tiles touch a boundary (thin or small grids, the boundary shells of a
   // decomposed run) -> [1]; else the default [0]
@@ -456,6 +457,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
   if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) == 1) ? 1 : 0;
+  if (const char* ev = getenv("EULERB200_CTAS")) c->ctas_target = std::max(1L, atol(ev));
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));

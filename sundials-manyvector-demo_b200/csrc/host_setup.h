@@ -142,7 +142,8 @@ struct LaunchGeom {
 // Tile shape: 256 threads; a full warp along x whenever the box is at least 31 cells
 // wide, otherwise the narrowest power of two that holds extent+1 faces (thin boxes such
 // as the 3-cell-wide hurricane plane then put the threads along y).
-inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256, int want_pair = 0)
+inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256, int want_pair = 0,
+                              long ctas_target = 5920)
 {
   LaunchGeom L;
   const long ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -158,10 +159,10 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   L.tx = tx; L.ty = ty;
   L.gx = (unsigned)((ex + tx - 2) / (tx - 1));
   L.gy = (unsigned)((ey + ty - 2) / (ty - 1));
-  // z-segments: enough CTAs for ~20 waves on 148 SMs x 2 resident CTAs, but at least 8
-  // cells per segment (one extra z-face is computed per segment)
+  // z-segments: enough CTAs for ~20 waves on 148 SMs x 2 resident CTAs (ctas_target; tuning knob
+  // EULERB200_CTAS), but at least 8 cells per segment (one extra z-face is computed per segment)
   const long tiles = (long)L.gx * L.gy;
-  long nseg = (5920 + tiles - 1) / tiles;
+  long nseg = (ctas_target + tiles - 1) / tiles;
   nseg = std::max(1L, std::min(nseg, (ez + 7) / 8));
   L.seg_len = (int)((ez + nseg - 1) / nseg);
   L.gz = (unsigned)((ez + L.seg_len - 1) / L.seg_len);

@@ -16,6 +16,10 @@ done
 for k in 0 1; do
   EULERB200_KERNEL=$k timeout 60 python tools/tune.py --n 512 512 512 --nchem 10 --variants 1 --steps 5 >> gpurun_out/r2_512_kernel.log 2>&1
 done
+# 3b. z-segment count: CTAs per launch aimed for (default 5920 -> 8 segments of 64 planes at 512^3)
+for ctas in 2960 3996 4440 8880; do
+  EULERB200_CTAS=$ctas timeout 60 python tools/tune.py --n 512 512 512 --nchem 10 --variants 1 --steps 5 2>&1 | sed "s/^/CTAS=$ctas /" >> gpurun_out/r2_512_ctas.log
+done
 # 4. race / memory check of the kernels on a small case (compute-sanitizer is in the CUDA toolkit)
 timeout 200 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -k "test_feuler_matches_oracle and 16" > gpurun_out/r2_racecheck.log 2>&1
 echo done > gpurun_out/r2_first_done.txt
