@@ -163,7 +163,7 @@ int eulerb200_stability_any(eulerb200_ctx* ctx, const double* const* w, double c
 /* Vector operations of the explicit driver loop (euler3D_main.cpp:357,387 hands these to
  * ARKODE, which evaluates them through N_VLinearCombination / N_VWrmsNorm on the
  * MPIManyVector); device pointers, one sub-vector per call.
- *   lincomb:     out[i] = sum_t coef[t] * x[t][i],  1 <= nterms <= 8, out may alias any x[t]
+ *   lincomb:     out[i] = sum_t coef[t] * x[t][i],  1 <= nterms <= 16, out may alias any x[t]
  *   wrms_accum:  *acc += sum_i (x[i] / (rtol*|y[i]| + atol))^2   (acc: device double) */
 int eulerb200_vec_lincomb(eulerb200_ctx* ctx, int32_t nterms, const double* coef, const double* const* x,
                           double* out, int64_t n, void* stream);

@@ -74,7 +74,7 @@ void* ARKStepCreate(ARKRhsFn fe, ARKRhsFn, realtype t0, N_Vector y0, SUNContext 
   N_VScale(1.0, y0, m->S.w.v);
   m->S.ytmp.v = clone(y0, ctx);
   m->S.yerr.v = clone(y0, ctx);
-  for (int i = 0; i < 7; i++) m->S.k[i].v = clone(y0, ctx);
+  for (int i = 0; i < 13; i++) m->S.k[i].v = clone(y0, ctx);
   return m;
 }
 void ARKStepFree(void** mem) { if (mem && *mem) { delete (ArkMem*)*mem; *mem = NULL; } }

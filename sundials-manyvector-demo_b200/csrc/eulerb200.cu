@@ -896,7 +896,7 @@ int eulerb200_stability_any(eulerb200_ctx* c, const double* const* w, double cfl
 int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x,
                           double* out, int64_t n, void* stream)
 {
-  if (!c || !coef || !x || !out || nterms < 1 || nterms > 8) return -1;
+  if (!c || !coef || !x || !out || nterms < 1 || nterms > 16) return -1;
   eb::LinCombArgs a;
   a.nterms = nterms;
   for (int t = 0; t < nterms; t++) { a.c[t] = coef[t]; a.x[t] = x[t]; }

@@ -54,8 +54,8 @@ __global__ void wavespeed_kernel(const double* __restrict__ rho, const double* _
 // is a multiple of the SM count.
 struct LinCombArgs {
   int nterms;
-  double c[8];
-  const double* x[8];
+  double c[16];
+  const double* x[16];
 };
 __global__ void lincomb_kernel(const LinCombArgs a, double* __restrict__ out, long n)
 {

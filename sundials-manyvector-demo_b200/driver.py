@@ -48,16 +48,33 @@ DORMAND_PRINCE = ([[], [0.2], [3.0 / 40, 9.0 / 40], [44.0 / 45, -56.0 / 15, 32.0
                    [35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84]],
                   [35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0.0],
                   [5179.0 / 57600, 0.0, 7571.0 / 16695, 393.0 / 640, -92097.0 / 339200, 187.0 / 2100, 1.0 / 40], 5, 4)
+VERNER = ([[], [1.0 / 6], [4.0 / 75, 16.0 / 75], [5.0 / 6, -8.0 / 3, 5.0 / 2],
+           [-165.0 / 64, 55.0 / 6, -425.0 / 64, 85.0 / 96],
+           [12.0 / 5, -8.0, 4015.0 / 612, -11.0 / 36, 88.0 / 255],
+           [-8263.0 / 15000, 124.0 / 75, -643.0 / 680, -81.0 / 250, 2484.0 / 10625, 0.0],
+           [3501.0 / 1720, -300.0 / 43, 297275.0 / 52632, -319.0 / 2322, 24068.0 / 84065, 0.0, 3850.0 / 26703]],
+          [3.0 / 40, 0.0, 875.0 / 2244, 23.0 / 72, 264.0 / 1955, 0.0, 125.0 / 11592, 43.0 / 616],
+          [13.0 / 160, 0.0, 2375.0 / 5984, 5.0 / 16, 12.0 / 85, 3.0 / 44, 0.0, 0.0], 6, 5)
+FEHLBERG_78 = ([[], [2.0 / 27], [1.0 / 36, 1.0 / 12], [1.0 / 24, 0.0, 1.0 / 8], [5.0 / 12, 0.0, -25.0 / 16, 25.0 / 16],
+                [1.0 / 20, 0.0, 0.0, 1.0 / 4, 1.0 / 5], [-25.0 / 108, 0.0, 0.0, 125.0 / 108, -65.0 / 27, 125.0 / 54],
+                [31.0 / 300, 0.0, 0.0, 0.0, 61.0 / 225, -2.0 / 9, 13.0 / 900],
+                [2.0, 0.0, 0.0, -53.0 / 6, 704.0 / 45, -107.0 / 9, 67.0 / 90, 3.0],
+                [-91.0 / 108, 0.0, 0.0, 23.0 / 108, -976.0 / 135, 311.0 / 54, -19.0 / 60, 17.0 / 6, -1.0 / 12],
+                [2383.0 / 4100, 0.0, 0.0, -341.0 / 164, 4496.0 / 1025, -301.0 / 82, 2133.0 / 4100, 45.0 / 82, 45.0 / 164, 18.0 / 41],
+                [3.0 / 205, 0.0, 0.0, 0.0, 0.0, -6.0 / 41, -3.0 / 205, -3.0 / 41, 3.0 / 41, 6.0 / 41, 0.0],
+                [-1777.0 / 4100, 0.0, 0.0, -341.0 / 164, 4496.0 / 1025, -289.0 / 82, 2193.0 / 4100, 51.0 / 82, 33.0 / 164, 12.0 / 41, 0.0, 1.0]],
+               [0.0, 0.0, 0.0, 0.0, 0.0, 34.0 / 105, 9.0 / 35, 9.0 / 35, 9.0 / 280, 9.0 / 280, 0.0, 41.0 / 840, 41.0 / 840],
+               [41.0 / 840, 0.0, 0.0, 0.0, 0.0, 34.0 / 105, 9.0 / 35, 9.0 / 35, 9.0 / 280, 9.0 / 280, 41.0 / 840, 0.0, 0.0], 8, 7)
 KNOTH_WOLKE = ([[], [1.0 / 3], [-3.0 / 16, 15.0 / 16]], [1.0 / 6, 3.0 / 10, 8.0 / 15], None, 3, 0)   # no embedding
 
 # ARKStepSetOrder(order): ARKODE's default explicit table of that order
-TABLES = {2: HEUN_EULER, 3: BOGACKI_SHAMPINE, 4: ZONNEVELD, 5: CASH_KARP}
+TABLES = {2: HEUN_EULER, 3: BOGACKI_SHAMPINE, 4: ZONNEVELD, 5: CASH_KARP, 6: VERNER, 8: FEHLBERG_78}
 # ARKStepSetTableNum(.., etable): ARKODE_ERKTableID values (arkode_butcher_erk.h, SUNDIALS 6.2) for
 # the tables whose coefficients are public textbook material.  The additive-method explicit parts
-# (2, 4, 9, 13 = ARK437L2SA, 14), Sayfy-Aburub (5), Verner (10) and Fehlberg 13-7-8 (11) are not
+# (2, 4, 9, 13 = ARK437L2SA, 14) and Sayfy-Aburub (5) are not
 # restated: the blast input files (etable = 13) run with order = 4 instead (inputs/*.txt).
 TABLES_BY_ID = {0: HEUN_EULER, 1: BOGACKI_SHAMPINE, 3: ZONNEVELD, 6: CASH_KARP, 7: FEHLBERG,
-                8: DORMAND_PRINCE, 12: KNOTH_WOLKE}
+                8: DORMAND_PRINCE, 10: VERNER, 11: FEHLBERG_78, 12: KNOTH_WOLKE}
 ERK_NONE = -1
 
 
@@ -65,7 +82,7 @@ def select_table(order, etable=ERK_NONE):
     """'order' overrides 'etable' (euler3D_main.cpp:207-213); order 0 and no table: order 4."""
     if order != 0:
         if order not in TABLES:
-            raise ValueError("explicit tables are provided for order 2, 3, 4 and 5")
+            raise ValueError("explicit tables are provided for order 2, 3, 4, 5, 6 and 8")
         return TABLES[order]
     if etable == ERK_NONE:
         return TABLES[4]

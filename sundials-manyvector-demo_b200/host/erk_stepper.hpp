@@ -7,7 +7,7 @@
 // is not ARKODE.
 //
 // Ops supplies:  typedef Vec;  void lincomb(Vec& out, int n, const double* c, Vec* const* v)
-// (out = sum c[q] * *v[q], n <= 8);  double wrms(const Vec& x, const Vec& y, rtol, atol)
+// (out = sum c[q] * *v[q], n <= 14);  double wrms(const Vec& x, const Vec& y, rtol, atol)
 // (N_VWrmsNorm of x with weights 1/(rtol |y| + atol));  int rhs(t, Vec& y, Vec& ydot);
 // int stability(Vec& w, t, cfl, double* dt).
 // ---------------------------------------------------------------------------
@@ -21,7 +21,7 @@ struct ErkStepper {
   typedef typename Ops::Vec Vec;
   Ops ops;
   Table T;
-  Vec w, ytmp, yerr, k[7];
+  Vec w, ytmp, yerr, k[13];
   double t = 0, h = 0, rtol = 1e-8, atol = 1e-12, hmin = 0, hmax = 0, h0 = 0, cfl = 0;
   int fixedstep = 0, mxsteps = 5000, maxnef = 7;
   double safety = 0.96, bias = 1.5, growth = 20.0, k1 = 0.58, k2 = 0.21, k3 = 0.1, etamx1 = 1e4, etamxf = 0.3;
@@ -55,17 +55,17 @@ struct ErkStepper {
   {
     for (int i = 0; i < T.s; i++) {
       if (i == 0) { f(t, w, k[0]); continue; }
-      double c[8]; Vec* v[8]; int n = 0; double ci = 0;
+      double c[16]; Vec* v[16]; int n = 0; double ci = 0;
       c[n] = 1.0; v[n++] = &w;
       for (int j = 0; j < i; j++) { ci += T.A[i][j]; if (T.A[i][j] != 0.0) { c[n] = hh * T.A[i][j]; v[n++] = &k[j]; } }
       lincomb(ytmp, n, c, v);
       f(t + ci * hh, ytmp, k[i]);
     }
-    { double c[8]; Vec* v[8]; int n = 0; c[n] = 1.0; v[n++] = &w;
+    { double c[16]; Vec* v[16]; int n = 0; c[n] = 1.0; v[n++] = &w;
       for (int j = 0; j < T.s; j++) if (T.b[j] != 0.0) { c[n] = hh * T.b[j]; v[n++] = &k[j]; }
       lincomb(ytmp, n, c, v); }
     if (fixedstep) return 0.0;
-    { double c[8]; Vec* v[8]; int n = 0;
+    { double c[16]; Vec* v[16]; int n = 0;
       for (int j = 0; j < T.s; j++) if (T.b[j] != T.bh[j]) { c[n] = hh * (T.b[j] - T.bh[j]); v[n++] = &k[j]; }
       lincomb(yerr, n, c, v); }
     return bias * wrms(yerr, w);

@@ -104,7 +104,7 @@ struct DeviceOps {
   void lincomb(Vec& out, int n, const double* c, Vec* const* v)
   {
     for (int f = 0; f < out.nsub; f++) {
-      const double* x[8];
+      const double* x[16];
       for (int q = 0; q < n; q++) x[q] = v[q]->sub[f];
       if (eulerb200_vec_lincomb(ctx, n, c, x, out.sub[f], out.len[f], NULL)) die("eulerb200_vec_lincomb");
     }
@@ -146,7 +146,7 @@ static void usage()
          "            --xlbc --xrbc --ylbc --yrbc --zlbc --zrbc   0 periodic, 1 Neumann, 2 Dirichlet, 3 reflecting\n"
          "units       --MassUnits --LengthUnits --TimeUnits\n"
          "run         --t0 --tf --nout, --showstats=1, --output=1 (write output-<n>.eb200), --restart=<n>\n"
-         "stepping    --order=2|3|4|5  or  --order=0 --etable=0|1|3|6|7|8|12   (order overrides etable)\n"
+         "stepping    --order=2|3|4|5|6|8  or  --order=0 --etable=0|1|3|6|7|8|10|11|12   (order overrides etable)\n"
          "            --rtol --atol --fixedstep=1 --hmax (the fixed step) --hmin --h0 --cfl --mxsteps --maxnef\n"
          "            --fixedstep=1 --htrans=<t>  adaptive (steps <= hmax) over (t0, t0+htrans], then fixed steps of hmax\n"
          "            --safety --bias --growth --k1 --k2 --k3 --etamx1 --etamxf   (0: ARKODE's default)\n");
@@ -185,7 +185,7 @@ int main(int argc, char** argv)
   if (P.nchem < 0 || P.nchem > 64) { fprintf(stderr, "illegal nchem = %d\n", P.nchem); return 1; }
   Table table;
   if (!make_table((int)in.get("order", 4), (int)in.get("etable", -1), table)) {
-    fprintf(stderr, "\nERROR: no explicit Butcher table for order = %d / etable = %d (orders 2-5; table ids 0 1 3 6 7 8 12)\n\n",
+    fprintf(stderr, "\nERROR: no explicit Butcher table for order = %d / etable = %d (orders 2-6, 8; table ids 0 1 3 6 7 8 10 11 12)\n\n",
             (int)in.get("order", 4), (int)in.get("etable", -1));
     return 1;
   }

@@ -71,7 +71,7 @@ int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches 
 int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x, double* out,
                           int64_t n, void*)
 {
-  if (!c || nterms < 1 || nterms > 8) return -1;
+  if (!c || nterms < 1 || nterms > 16) return -1;
   emu_lincomb(nterms, coef, x, out, (long)n);
   c->launches++;
   return 0;

@@ -158,32 +158,44 @@ def _order_residuals(A, b):
     return {p: max(abs(x - y) for x, y in v) for p, v in cond.items()}
 
 
-@pytest.mark.parametrize("tid", [0, 1, 3, 6, 7, 8, 12])
+@pytest.mark.parametrize("tid", [0, 1, 3, 6, 7, 8, 10, 11, 12])
 def test_erk_tables_by_id_satisfy_their_order_conditions(pkg, tid):
     """ARKStepSetTableNum ids (euler3D_main.cpp:211-212): the method has order p, the
     embedding order q -- and not one more."""
     A, b, bhat, p, q = pkg.driver.TABLES_BY_ID[tid]
-    res = _order_residuals(A, b)
-    assert all(res[o] < 1e-14 for o in range(1, p + 1)), res
-    assert p == 5 or res[p + 1] > 1e-6
+    res = _order_residuals(A, b)                       # all 17 conditions up to order 5
+    assert all(res[o] < 1e-14 for o in range(1, min(p, 5) + 1)), res
+    assert p >= 5 or res[p + 1] > 1e-6
     if bhat is not None:
         rh = _order_residuals(A, bhat)
-        assert all(rh[o] < 1e-14 for o in range(1, q + 1)), rh
-        assert rh[q + 1] > 1e-6
+        assert all(rh[o] < 1e-14 for o in range(1, min(q, 5) + 1)), rh
+        assert q >= 5 or rh[q + 1] > 1e-6
+    if p > 5:                                          # beyond: the quadrature and tall-tree conditions
+        M = np.zeros((len(b), len(b)))
+        for i, row in enumerate(A):
+            M[i, :len(row)] = row
+        c, bb = M.sum(axis=1), np.asarray(b)
+        assert all(abs(bb @ c ** (o - 1) - 1.0 / o) < 1e-14 for o in range(6, p + 1))
+        tall, fact = c.copy(), 1.0
+        for o in range(2, p + 1):
+            fact *= o
+            assert abs(bb @ tall - 1.0 / fact) < 1e-14
+            tall = M @ tall
+        assert abs(bb @ c ** p - 1.0 / (p + 1)) > 1e-7 or tid == 11      # (Fehlberg 7(8) integrates quadratures exactly)
 
 
-@pytest.mark.parametrize("tid", [3, 6, 8, 12])
+@pytest.mark.parametrize("tid", [3, 6, 8, 10, 11, 12])
 def test_erk_tables_observed_order(pkg, tid):
     from helpers import NpVec
     p = pkg.driver.TABLES_BY_ID[tid][3]
     sols = []
-    for h in (0.1, 0.05, 0.025):
+    for h in {6: (0.2, 0.1, 0.05), 8: (0.5, 0.25, 0.125)}.get(p, (0.1, 0.05, 0.025)):
         opts = pkg.driver.ARKODEParameters(order=0, etable=tid, fixedstep=1, hmax=h)
         step = pkg.driver.ERKStep(_OdeOps(), 0.0, NpVec([np.array([0.5, 1.0])]), opts)
         ret, t = step.evolve(1.0)
         assert ret == 0 and t == 1.0
         sols.append(step.w.sub[0].copy())
-    opts = pkg.driver.ARKODEParameters(order=0, etable=8, rtol=1e-13, atol=1e-14)
+    opts = pkg.driver.ARKODEParameters(order=0, etable=11, fixedstep=1, hmax=1.0 / 64)      # order 8, 64 steps
     ref = pkg.driver.ERKStep(_OdeOps(), 0.0, NpVec([np.array([0.5, 1.0])]), opts)
     assert ref.evolve(1.0)[0] == 0
     errs = [np.abs(s - ref.w.sub[0]).max() for s in sols]
@@ -211,7 +223,7 @@ def test_native_driver_tables_equal_the_python_tables(pkg, tmp_path):
     subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", os.path.join(here, "..", "sundials-manyvector-demo_b200", "host"),
                            "-o", exe, os.path.join(here, "native_tables_check.cpp")])
     d = pkg.driver
-    for order, etable in [(2, -1), (3, -1), (4, -1), (5, -1), (4, 8), (0, -1)] + [(0, t) for t in sorted(d.TABLES_BY_ID)]:
+    for order, etable in [(2, -1), (3, -1), (4, -1), (5, -1), (6, -1), (8, -1), (4, 8), (0, -1)] + [(0, t) for t in sorted(d.TABLES_BY_ID)]:
         out = subprocess.run([exe, str(order), str(etable)], capture_output=True, text=True, check=True).stdout.split("\n")
         A, b, bhat, p, q = d.select_table(order, etable)
         s = len(b)
@@ -221,5 +233,5 @@ def test_native_driver_tables_equal_the_python_tables(pkg, tmp_path):
             assert list(M[i, :len(A[i])]) == list(A[i]) and not M[i, len(A[i]):].any()
         assert [float(x) for x in out[1 + s].split()] == list(b)
         assert [float(x) for x in out[2 + s].split()] == (list(bhat) if bhat is not None else [0.0] * s)
-    for order, etable in [(6, -1), (0, 13), (0, 2)]:
+    for order, etable in [(7, -1), (0, 13), (0, 2)]:
         assert subprocess.run([exe, str(order), str(etable)], capture_output=True, text=True).stdout.strip() == "none"

@@ -149,7 +149,7 @@ def test_native_driver_help_and_option_errors_need_no_gpu(pkg):
     import subprocess
     exe = os.path.join(ROOT, "sundials-manyvector-demo_b200", "euler3d_b200")
     out = subprocess.run([exe, "--help"], capture_output=True, text=True)
-    assert out.returncode == 0 and "--etable=0|1|3|6|7|8|12" in out.stdout and "primordial_blast" in out.stdout
+    assert out.returncode == 0 and "--etable=0|1|3|6|7|8|10|11|12" in out.stdout and "primordial_blast" in out.stdout
     for args, msg in ((["--order=7"], "no explicit Butcher table"), (["--order=0", "--etable=13"], "no explicit Butcher table"),
                       (["--order=0", "--etable=12"], "needs fixedstep = 1")):
         out = subprocess.run([exe] + args, capture_output=True, text=True)

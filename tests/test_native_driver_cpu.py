@@ -43,7 +43,9 @@ def advection_state(n, axis):
 @pytest.mark.parametrize("sel,kw", [(["--order=4"], dict(order=4)), (["--order=3"], dict(order=3)),
                                     (["--order=0", "--etable=8"], dict(order=0, etable=8)),
                                     (["--order=0", "--etable=6"], dict(order=0, etable=6)),
-                                    (["--order=0", "--etable=12"], dict(order=0, etable=12))])
+                                    (["--order=0", "--etable=12"], dict(order=0, etable=12)),
+                                    (["--order=6"], dict(order=6)),                       # Verner 8-5-6
+                                    (["--order=0", "--etable=11"], dict(order=0, etable=11))])   # Fehlberg 13-7-8: 14-term combinations
 def test_fixed_step_runs_equal_the_python_driver_with_the_oracle_rhs(pkg, port, exe, tmp_path, sel, kw):
     """linear_advection_y, 3 x 24 x 3, 20 fixed steps with the chosen Butcher table: the state the
     native driver writes equals the Python driver's (numpy stage arithmetic, oracle fEuler) to 1e-12."""
