@@ -80,9 +80,36 @@ EB_HD double fast_rcp(double b)
 // the samples reversed for the right-biased ("f-") form.
 //   result = q2 + [ a1 (q1-q2) + a3 (q3-q2) ] / (a1+a2+a3),  a_k = d_k / (eps+beta_k)^2
 // with q1-q2 = -(D1-D2)/6 and q3-q2 = (D3-D2)/3 (D_k the second differences).
+// Everything is built from the four first differences d_j = v_{j+1} - v_j (40 FP64-pipe
+// instructions with two Newton steps in the reciprocal):
+//   D1 = d3-d2, D2 = d2-d1, D3 = d1-d0;  E1 = d3-3 d2, E2 = -(d1+d2), E3 = 3 d1-d0;
+//   q2 = v2 + (2 d2 + d1)/6;  numerator and denominator scaled by 10.
+#ifndef EB_WENO_CLASSIC
 EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
 {
   // beta_k/bc = D_k^2 + (0.25/bc) E_k^2; the common factor 1/bc cancels in the weight ratios
+  const double c2 = 0.25 / (13.0 / 12.0);
+  const double epsb = (4.0 * 1e-6) / (13.0 / 12.0);
+  const double d0 = v1 - v0, d1 = v2 - v1, d2 = v3 - v2, d3 = v4 - v3;
+  const double D1 = d3 - d2, D2 = d2 - d1, D3 = d1 - d0;
+  const double E1 = fma(-3.0, d2, d3);
+  const double E2 = d1 + d2;
+  const double E3 = fma(3.0, d1, -d0);
+  const double b1 = fma(D1, D1, fma(c2 * E1, E1, epsb));
+  const double b2 = fma(D2, D2, fma(c2 * E2, E2, epsb));
+  const double b3 = fma(D3, D3, fma(c2 * E3, E3, epsb));
+  const double s1 = b1 * b1, s2 = b2 * b2, s3 = b3 * b3;
+  const double P1 = s2 * s3, P2 = s1 * s3, P3 = s1 * s2;
+  const double den = fma(3.0, P1, fma(6.0, P2, P3));
+  const double t3 = P3 * (D3 - D2), t1 = P1 * (D1 - D2);
+  const double num = fma(1.0 / 3.0, t3, -0.5 * t1);
+  const double q2 = fma(1.0 / 6.0, fma(2.0, d2, d1), v2);
+  return fma(num, EB_WENO_RCP(den), q2);
+}
+#else
+// the first formulation (43 instructions), kept for A/B runs: -DEB_WENO_CLASSIC
+EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
+{
   const double c2 = 0.25 / (13.0 / 12.0);
   const double epsb = (4.0 * 1e-6) / (13.0 / 12.0);
   const double D1 = fma(-2.0, v3, v2) + v4;
@@ -101,6 +128,7 @@ EB_HD double weno5(double v0, double v1, double v2, double v3, double v4)
   const double q2 = fma(1.0 / 3.0, v3, fma(5.0 / 6.0, v2, (-1.0 / 6.0) * v1));
   return fma(num, EB_WENO_RCP(den), q2);
 }
+#endif
 
 // Roe-averaged face state and the projection coefficients derived from it.
 struct Eigen {

@@ -158,11 +158,13 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set[3] = {0, 0, 0}, carveout_for[3] = {(size_t)-1, (size_t)-1, (size_t)-1};   // per kernel instantiation
+  size_t max_smem_set[4][3][3] = {}, carveout_for[4][3][3] = {};   // per kernel instantiation [variant][kind][part]
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
   long ctas_target = 5920;       // EULERB200_CTAS: CTAs a launch aims for when cutting z-segments (tuning)
   int force_kernel = 0;          // EULERB200_KERNEL=1: allow the AG instantiation for boundary-heavy launches
   int variant = 0;
+  int split = 0;                 // EULERB200_SPLIT=1: fluid fields and species in separate launches
+  int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
   int pair_sync = 2;                                       // EULERB200_PAIR: 0 CTA-wide barriers, 1/2 pairwise row rendezvous (rhs_kernel.cuh)
@@ -171,22 +173,26 @@ struct eulerb200_ctx {
 namespace {
 
 // Compiled variants of the RHS kernel: threads per CTA and resident CTAs per SM fix the
-// register budget (65536 / (threads * CTAs)).  EULERB200_VARIANT selects one by index for
-// tuning runs; the default is the fastest measured on B200 (profiles/).
+// register budget (65536 / (threads * CTAs)).  EULERB200_VARIANT (fused launch) and
+// EULERB200_VARIANT_F / _T (fluid / species launches of the split mode) select one by index for
+// tuning runs; the defaults are the fastest measured on B200 (profiles/).
 struct KernelVariant {
-  // [0] the measured default; [1] AG: boundary tiles read the per-cell arrays where valid (for
-  // launches that are mostly boundary tiles; opt-in with EULERB200_KERNEL=1 until it has been
-  // timed on a B200); [2] GW: G taken from wdot (hook-assigned forcing)
-  void (*fn[3])(const eb::RhsParams);
+  // fn[kind][part].  kind 0: the default; 1: AG, boundary tiles read the per-cell arrays where valid
+  // (for launches that are mostly boundary tiles); 2: GW, G taken from wdot (hook-assigned forcing).
+  // part: eb::PART_ALL / PART_FLUID / PART_TRACERS.  nullptr: not compiled (launch_box falls back).
+  void (*fn[3][3])(const eb::RhsParams);
   int threads;
   const char* name;
 };
-#define EB_KERNELS(T, B) {eb::rhs_fused_kernel<T, B>, eb::rhs_fused_kernel<T, B, false, true>, eb::rhs_fused_kernel<T, B, true, false>}
+#define EB_K(T, B, GW, AG, PART) eb::rhs_fused_kernel<T, B, GW, AG, eb::PART>
+#define EB_KIND(T, B, GW, AG) {EB_K(T, B, GW, AG, PART_ALL), EB_K(T, B, GW, AG, PART_FLUID), EB_K(T, B, GW, AG, PART_TRACERS)}
+#define EB_KERNELS_FULL(T, B) {EB_KIND(T, B, false, false), EB_KIND(T, B, false, true), EB_KIND(T, B, true, false)}
+#define EB_KERNELS_PLAIN(T, B) {EB_KIND(T, B, false, false), {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
 const KernelVariant kVariants[] = {
-    {EB_KERNELS(256, 1), 256, "256x1 (<=255 regs)"},
-    {EB_KERNELS(384, 1), 384, "384x1 (<=168 regs)"},
-    {EB_KERNELS(512, 1), 512, "512x1 (<=128 regs)"},
-    {EB_KERNELS(256, 2), 256, "256x2 (<=128 regs)"},
+    {EB_KERNELS_PLAIN(256, 1), 256, "256x1 (<=255 regs)"},
+    {EB_KERNELS_FULL(384, 1), 384, "384x1 (<=168 regs)"},
+    {EB_KERNELS_FULL(512, 1), 512, "512x1 (<=128 regs)"},
+    {EB_KERNELS_PLAIN(640, 1), 640, "640x1 (<=96 regs)"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultVariant = 1;
@@ -235,39 +241,59 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   return P;
 }
 
-// Evaluate the cells of [lo,hi) (clipped to non-empty) on `s`.
+// Evaluate the cells of [lo,hi) (clipped to non-empty) on `s`: one fused launch, or (split mode,
+// nchem > 0) a fluid launch followed by a species launch.
+int launch_part(eulerb200_ctx* c, eb::RhsParams P, int kind, int part, cudaStream_t s)
+{
+  const int nf = part == eb::PART_ALL ? 5 + P.nchem : (part == eb::PART_FLUID ? 5 : P.nchem);
+  const int vi = c->variant_part[part];
+  const KernelVariant& V = kVariants[vi];
+  void (*const fn)(const eb::RhsParams) = V.fn[kind][part];
+  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, nf, V.threads, c->pair_sync, c->ctas_target);
+  P.seg_len = L.seg_len;
+  P.pair_sync = L.pair;
+  size_t& smem_set = c->max_smem_set[vi][kind][part];
+  size_t& carve_for = c->carveout_for[vi][kind][part];
+  if (L.smem > smem_set) {
+    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    smem_set = L.smem;
+  }
+  if (L.smem != carve_for) {
+    // the stencil loads live in L1: ask for the smallest shared-memory carve-out that holds one CTA
+    // (+1 KB the system reserves per CTA) and leave the rest of the 256 KB to L1
+    const int pct = (int)std::min<size_t>(100, (100 * (L.smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    carve_for = L.smem;
+  }
+  fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long hi[3], cudaStream_t s)
 {
   for (int d = 0; d < 3; d++) {
     if (hi[d] <= lo[d]) return 0;
     P.lo[d] = lo[d]; P.hi[d] = hi[d];
   }
-  const KernelVariant& V = kVariants[c->variant];
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, V.threads, c->pair_sync, c->ctas_target);
-  // which instantiation: hook-assigned forcing -> [2]; with EULERB200_KERNEL=1 a launch in which a
+  // which instantiation: hook-assigned forcing -> kind 2; with EULERB200_KERNEL=1 a launch in which a
   // quarter or more of the tiles touch a boundary (thin or small grids, the boundary shells of a
-  // decomposed run) -> [1]; else the default [0]
-  int gw = 0;
-  if (c->forcing_in_wdot) gw = 2;
-  else if (c->force_kernel == 1 && c->use_aux && eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) gw = 1;
-  void (*const fn)(const eb::RhsParams) = V.fn[gw];
-  P.seg_len = L.seg_len;
-  P.pair_sync = L.pair;
-  if (L.smem > c->max_smem_set[gw]) {
-    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    c->max_smem_set[gw] = L.smem;
+  // decomposed run) -> kind 1; else the default kind 0
+  int kind = 0;
+  if (c->forcing_in_wdot) kind = 2;
+  else if (c->force_kernel == 1 && c->use_aux) {
+    const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, 5 + P.nchem, kVariants[c->variant_part[0]].threads, c->pair_sync, c->ctas_target);
+    if (eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) kind = 1;
   }
-  if (L.smem != c->carveout_for[gw]) {
-    // the stencil loads live in L1: ask for the smallest shared-memory carve-out that holds one CTA
-    // (+1 KB the system reserves per CTA) and leave the rest of the 256 KB to L1
-    const int pct = (int)std::min<size_t>(100, (100 * (L.smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
-    EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    c->carveout_for[gw] = L.smem;
+  const bool split = c->split && P.nchem > 0 && kVariants[c->variant_part[1]].fn[kind][1] && kVariants[c->variant_part[2]].fn[kind][2];
+  if (split) {
+    int rc = launch_part(c, P, kind, eb::PART_FLUID, s);
+    if (rc) return rc;
+    return launch_part(c, P, kind, eb::PART_TRACERS, s);
   }
-  fn<<<dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, s>>>(P);
-  c->launches++;
-  EB_CUDA(c, cudaGetLastError());
-  return 0;
+  if (!kVariants[c->variant_part[0]].fn[kind][0]) c->variant_part[0] = kDefaultVariant;   // kind compiled for the default only
+  return launch_part(c, P, kind, eb::PART_ALL, s);
 }
 
 // Per-cell derived values for the z-planes [k0, k1) of the state in P.
@@ -435,6 +461,12 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     const int v = atoi(ev);
     if (v >= 0 && v < kNumVariants) c->variant = v;
   }
+  c->variant_part[0] = c->variant;
+  c->variant_part[1] = c->variant_part[2] = kDefaultVariant;
+  if (const char* ev = getenv("EULERB200_VARIANT_F")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[1] = v; }
+  if (const char* ev = getenv("EULERB200_VARIANT_T")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[2] = v; }
+  if (const char* ev = getenv("EULERB200_SPLIT")) c->split = atoi(ev) != 0;
+  for (int a_ = 0; a_ < 4; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
   if (cfg->device >= 0) {
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }

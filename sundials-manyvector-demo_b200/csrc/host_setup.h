@@ -142,7 +142,8 @@ struct LaunchGeom {
 // Tile shape: 256 threads; a full warp along x whenever the box is at least 31 cells
 // wide, otherwise the narrowest power of two that holds extent+1 faces (thin boxes such
 // as the 3-cell-wide hurricane plane then put the threads along y).
-inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int threads = 256, int want_pair = 0,
+// nf: fields the launch evaluates (NVAR for the fused launch, 5 / nchem for the fluid / species launches)
+inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nf, int threads = 256, int want_pair = 0,
                               long ctas_target = 5920)
 {
   LaunchGeom L;
@@ -154,7 +155,7 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   // three flux arrays [NVAR][threads] must fit the 227 KB of shared memory a CTA can opt in to:
   // many species (NVAR up to 64) get a flatter tile
   // (FX and ZLO skip the face-only top row: 3 ty - 2 rows of NVAR x tx doubles in all)
-  const size_t smem_max = (size_t)227 * 1024, per_row = (size_t)(5 + nchem) * tx * sizeof(double);
+  const size_t smem_max = (size_t)227 * 1024, per_row = (size_t)nf * tx * sizeof(double);
   while (ty > 2 && per_row * (3 * ty - 2) > smem_max) ty--;
   L.tx = tx; L.ty = ty;
   L.gx = (unsigned)((ex + tx - 2) / (tx - 1));
@@ -167,8 +168,8 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nchem, int
   L.seg_len = (int)((ez + nseg - 1) / nseg);
   L.gz = (unsigned)((ez + L.seg_len - 1) / L.seg_len);
   // pairwise row rendezvous (rhs_fused_kernel): rows must be warps, one named barrier per row
-  // pair (ids 1..15), and the second FY buffer has to fit the 227 KB a CTA can have
-  L.pair = (tx == 32 && ty >= 2 && ty <= 15) ? want_pair : 0;
+  // pair (ids 1..15: at most 16 rows), and the second FY buffer has to fit the 227 KB a CTA can have
+  L.pair = (tx == 32 && ty >= 2 && ty <= 16) ? want_pair : 0;
   if (L.pair == 1 && per_row * (4 * ty - 2) > smem_max) L.pair = 2;
   L.smem = per_row * ((L.pair == 1 ? 4 : 3) * ty - 2);
   return L;

@@ -33,6 +33,13 @@ namespace eb {
 
 enum { GHOST_MAP = 0, GHOST_BUF = 1 };
 
+// Which fields a launch evaluates.  PART_ALL: one fused launch.  PART_FLUID / PART_TRACERS: the five
+// fluid fields and the advected species in separate launches -- the species need only the face-local
+// alpha and the normal velocities of the fluid part (utilities.cpp:368-380), which cost ~25 FP64
+// instructions per face to rebuild from the per-cell arrays, and without the fluid face's ~170
+// registers the species launch runs at a higher occupancy.
+enum { PART_ALL = 0, PART_FLUID = 1, PART_TRACERS = 2 };
+
 // How stencil positions beyond one side of the owned range along an axis are resolved.
 struct GhostFace {
   int mode;            // GHOST_MAP: owned index = a + b*pos ; GHOST_BUF: halo buffer
@@ -134,11 +141,31 @@ EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
   return P.w[field][pt.off];
 }
 
-// Face flux of all NVAR fields for the face below cell (i,j,k) along `dir`.  Each flux is
+// Normal velocity u = mn/rho and sound speed c of one stencil point, for launches that evaluate
+// the species only (PART_TRACERS): from the per-cell arrays where they are valid (owned points, and
+// ghost points that are an owned cell with at most its momenta negated), else from the five fluid
+// values of the point (halo slabs, Dirichlet ghosts, or no per-cell arrays at all).
+template <bool GEN>
+EB_HD void point_uc(const RhsParams& P, const StencilPt& pt, int fn, int f1, int f2, double& u, double& c)
+{
+  const bool owned = !GEN || pt.src < 0;
+  if (P.aux[0] != nullptr && owned && (!GEN || (pt.neg & 0x11u) == 0u)) {
+    u = load_fluid<GEN>(P, pt, fn) * P.aux[0][pt.off];
+    c = P.aux[2][pt.off];
+  } else {
+    const double mn = load_fluid<GEN>(P, pt, fn);
+    const CellAux a = cell_aux(P.gamma, load_fluid<GEN>(P, pt, 0), mn, load_fluid<GEN>(P, pt, f1),
+                               load_fluid<GEN>(P, pt, f2), load_fluid<GEN>(P, pt, 4));
+    u = mn * a.rinv;
+    c = a.c;
+  }
+}
+
+// Face flux of the fields of PART for the face below cell (i,j,k) along `dir`.  Each flux is
 // handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
-// i.e. of cell (i,j,k) itself.
-template <bool GEN, bool AG, class Emit>
+// i.e. of cell (i,j,k) itself (0 from a species-only launch: the fluid launch reports them).
+template <bool GEN, bool AG, int PART, class Emit>
 EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
   StencilPt pt[6];
@@ -149,61 +176,76 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   const int f1 = (dir == 1) ? 1 : 2;
   const int f2 = (dir == 2) ? 1 : 3;
 
-  FluidStencil s;
-#pragma unroll
-  for (int l = 0; l < 6; l++) {
-    s.r[l] = load_fluid<GEN>(P, pt[l], 0);
-    s.mn[l] = load_fluid<GEN>(P, pt[l], fn);
-    s.m1[l] = load_fluid<GEN>(P, pt[l], f1);
-    s.m2[l] = load_fluid<GEN>(P, pt[l], f2);
-    s.e[l] = load_fluid<GEN>(P, pt[l], 4);
-  }
-  // Per-cell derived values: interior CTAs read what aux_kernel stored; CTAs that touch
-  // ghost or halo points derive them from the (sign-mapped) state they just loaded.
-  if (!GEN && P.aux[0] != nullptr) {
+  double alpha, u[6];
+  int bits = 0;
+  if (PART != PART_TRACERS) {
+    FluidStencil s;
 #pragma unroll
     for (int l = 0; l < 6; l++) {
-      s.rinv[l] = P.aux[0][pt[l].off];
-      s.p[l] = P.aux[1][pt[l].off];
-      s.c[l] = P.aux[2][pt[l].off];
+      s.r[l] = load_fluid<GEN>(P, pt[l], 0);
+      s.mn[l] = load_fluid<GEN>(P, pt[l], fn);
+      s.m1[l] = load_fluid<GEN>(P, pt[l], f1);
+      s.m2[l] = load_fluid<GEN>(P, pt[l], f2);
+      s.e[l] = load_fluid<GEN>(P, pt[l], 4);
     }
-    s.srL = P.aux[3][pt[2].off];
-    s.srR = P.aux[3][pt[3].off];
-  } else {
-    // Tiles that touch a boundary (AG instantiation, chosen for launches where such tiles are
-    // many: thin grids, small grids, the boundary shells of a decomposed run): owned points, and
-    // ghost points that are an owned cell with at most its momenta negated (periodic wrap, Neumann,
-    // reflecting: 1/rho, p, c, sqrt(rho) are even in the momenta), still read the per-cell arrays;
-    // only Dirichlet ghosts (rho, e_t negated) and halo-slab points are derived here.
-    const bool have_aux = AG && P.aux[0] != nullptr;
+    // Per-cell derived values: interior CTAs read what aux_kernel stored; CTAs that touch
+    // ghost or halo points derive them from the (sign-mapped) state they just loaded.
+    if (!GEN && P.aux[0] != nullptr) {
 #pragma unroll
-    for (int l = 0; l < 6; l++) {
-      if (have_aux && pt[l].src < 0 && (pt[l].neg & 0x11u) == 0u) {
+      for (int l = 0; l < 6; l++) {
         s.rinv[l] = P.aux[0][pt[l].off];
         s.p[l] = P.aux[1][pt[l].off];
         s.c[l] = P.aux[2][pt[l].off];
-        if (l == 2) s.srL = P.aux[3][pt[l].off];
-        if (l == 3) s.srR = P.aux[3][pt[l].off];
-      } else {
-        const CellAux a = cell_aux(P.gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
-        s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
-        if (l == 2) s.srL = a.sr;
-        if (l == 3) s.srR = a.sr;
       }
+      s.srL = P.aux[3][pt[2].off];
+      s.srR = P.aux[3][pt[3].off];
+    } else {
+      // Tiles that touch a boundary (AG instantiation, chosen for launches where such tiles are
+      // many: thin grids, small grids, the boundary shells of a decomposed run): owned points, and
+      // ghost points that are an owned cell with at most its momenta negated (periodic wrap, Neumann,
+      // reflecting: 1/rho, p, c, sqrt(rho) are even in the momenta), still read the per-cell arrays;
+      // only Dirichlet ghosts (rho, e_t negated) and halo-slab points are derived here.
+      const bool have_aux = AG && P.aux[0] != nullptr;
+#pragma unroll
+      for (int l = 0; l < 6; l++) {
+        if (have_aux && pt[l].src < 0 && (pt[l].neg & 0x11u) == 0u) {
+          s.rinv[l] = P.aux[0][pt[l].off];
+          s.p[l] = P.aux[1][pt[l].off];
+          s.c[l] = P.aux[2][pt[l].off];
+          if (l == 2) s.srL = P.aux[3][pt[l].off];
+          if (l == 3) s.srR = P.aux[3][pt[l].off];
+        } else {
+          const CellAux a = cell_aux(P.gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
+          s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
+          if (l == 2) s.srL = a.sr;
+          if (l == 3) s.srR = a.sr;
+        }
+      }
+    }
+
+    double f[5];
+    fluid_face(s, P.gamma, f, alpha, u);
+    bits = ((s.r[3] > 0.0) ? 0 : 1) | ((s.e[3] > 0.0) ? 0 : 2) | ((s.p[3] > 0.0) ? 0 : 4);
+
+    emit(0, f[0]);
+    emit(fn, f[1]);
+    emit(f1, f[2]);
+    emit(f2, f[3]);
+    emit(4, f[4]);
+  } else {
+    // species-only launch: the face-local alpha = max_j |u_j| + c_j (utilities.cpp:368-380) and the
+    // normal velocities, exactly as fluid_face forms them
+    alpha = 0.0;
+#pragma unroll
+    for (int l = 0; l < 6; l++) {
+      double c;
+      point_uc<GEN>(P, pt[l], fn, f1, f2, u[l], c);
+      const double a = fabs(u[l]) + c;
+      alpha = (alpha < a) ? a : alpha;
     }
   }
 
-  double f[5], alpha, u[6];
-  fluid_face(s, P.gamma, f, alpha, u);
-  const int bits = ((s.r[3] > 0.0) ? 0 : 1) | ((s.e[3] > 0.0) ? 0 : 2) | ((s.p[3] > 0.0) ? 0 : 4);
-
-  emit(0, f[0]);
-  emit(fn, f[1]);
-  emit(f1, f[2]);
-  emit(f2, f[3]);
-  emit(4, f[4]);
-
-  if (P.nchem > 0) {
+  if (PART != PART_FLUID && P.nchem > 0) {
     double up[6], um[6];
 #pragma unroll
     for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
@@ -262,10 +304,10 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
   return bits;
 }
 
-template <bool AG, class Emit>
+template <bool AG, int PART, class Emit>
 EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, long k, Emit emit)
 {
-  return gen ? face_all<true, AG>(P, dir, i, j, k, emit) : face_all<false, AG>(P, dir, i, j, k, emit);
+  return gen ? face_all<true, AG, PART>(P, dir, i, j, k, emit) : face_all<false, AG, PART>(P, dir, i, j, k, emit);
 }
 
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
@@ -297,10 +339,11 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 }
 #endif
 
-// Dynamic shared memory: FX [NVAR][T-TX], FY [NVAR][T] (exchanged with the +x / +y neighbour
-// thread) and ZLO [NVAR][T-TX] (thread-private: flux through the z-face below); 127.5 KB at
-// NVAR = 15 with 384 threads, which leaves the SM its 132 KB carve-out and 124 KB of L1 -- the
-// stencil loads live in L1, and its size shows directly in the kernel time.
+// Dynamic shared memory: FX [NF][T-TX], FY [NF][T] (exchanged with the +x / +y neighbour
+// thread) and ZLO [NF][T-TX] (thread-private: flux through the z-face below), NF the number of
+// fields of the launch (NVAR, 5, or nchem); 127.5 KB at NF = 15 with 384 threads, which leaves
+// the SM its 132 KB carve-out and 124 KB of L1 -- the stencil loads live in L1, and its size shows
+// directly in the kernel time.
 //
 // Synchronisation.  Default: two CTA-wide barriers per plane (fluxes published / consumed).
 // With P.pair_sync (tile rows are warps, TX == 32): FX never leaves the warp (lane l reads lane
@@ -315,21 +358,24 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // GW: the forcing is not the per-field constant of the config; the caller has run the
 // external_forces hook into wdot (utilities.cpp:65) and every store is wdot = wdot - div.
 // AG: boundary tiles read the per-cell arrays wherever they are valid (see face_all).
-template <int MAXT, int MINB, bool GW = false, bool AG = false>
+// PART: all fields, or the fluid fields / the species only (two launches, see the enum).
+template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
   const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
-  const int nv = 5 + P.nchem;
+  // fields of this launch: v0 .. v0+nf-1 in the reference's order
+  const int v0 = (PART == PART_TRACERS) ? 5 : 0;
+  const int nf = (PART == PART_ALL) ? 5 + P.nchem : (PART == PART_FLUID ? 5 : P.nchem);
   const bool pair = P.pair_sync != 0;
   const bool two_fy = P.pair_sync == 1;
-  // the face-only top row of the tile never touches FX / ZLO: those arrays are [NVAR][TR]
+  // the face-only top row of the tile never touches FX / ZLO: those arrays are [NF][TR]
   const int TR = T - TX;
-  double* FX = smem + t;
-  double* FY = smem + (long)nv * TR + t;
-  long fy_flip = two_fy ? (long)nv * T : 0;         // signed distance to the other FY buffer
-  double* ZLO = smem + (long)nv * (TR + (two_fy ? 2L : 1L) * T) + t;
+  double* FX = smem + t - (long)v0 * TR;               // indexed with the global field number v
+  double* FY = smem + (long)nf * TR + t - (long)v0 * T;
+  long fy_flip = two_fy ? (long)nf * T : 0;         // signed distance to the other FY buffer
+  double* ZLO = smem + (long)nf * (TR + (two_fy ? 2L : 1L) * T) + t - (long)v0 * TR;
 
   const long ti0 = P.lo[0] + (long)blockIdx.x * (TX - 1);
   const long tj0 = P.lo[1] + (long)blockIdx.y * (TY - 1);
@@ -351,17 +397,17 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
   // z-face below the first plane of the segment
   if (owns)
-    face_dispatch<AG>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
+    face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
                   [&](int v, double x) { ZLO[v * TR] = x; });
 
   for (long k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (need_x) {
-      const int bits = face_dispatch<AG>(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
+      const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
       if (owns) mask |= bits;
     }
     if (need_y)
-      face_dispatch<AG>(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
+      face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
     if (pair) {
       if (ty > 0) eb_bar_sync(ty, 64);
       if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
@@ -373,7 +419,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
     if (owns) {
       const long cell = i + P.nx * (j + P.ny * k);
-      face_dispatch<AG>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
+      face_dispatch<AG, PART>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
                     [&](int v, double zup) {
                       const double div = ((FX[v * TR + 1] - FX[v * TR]) * P.rdx
                                         + (FY[v * T + TX] - FY[v * T]) * P.rdy)
@@ -416,7 +462,7 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     }
   }
 
-  if (mask) atomicOr(P.state_flag, mask);
+  if (PART != PART_TRACERS && mask) atomicOr(P.state_flag, mask);
 }
 
 #endif  // __CUDACC__ || EB_CUDA_EMU

@@ -10,7 +10,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen)
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -42,14 +42,28 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.state_flag = &flag;
   const long full_lo[3] = {0, 0, 0}, full_hi[3] = {P.nx, P.ny, P.nz};
   for (int d = 0; d < 3; d++) { P.lo[d] = lo ? lo[d] : full_lo[d]; P.hi[d] = hi ? hi[d] : full_hi[d]; }
-  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, P.nchem, threads, pair);
-  P.pair_sync = L.pair;
-  if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
-  P.seg_len = L.seg_len;
-  // the three instantiations launch_box() chooses from on the device
-  if (g_in_wdot) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, true, false>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
-  else if (aux_in_gen) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, false, true>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
-  else cuda_emu::launch(eb::rhs_fused_kernel<256, 1>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+  // the launches launch_box() makes on the device: one fused launch, or (split) fluid then species
+  const int parts[2] = {split && P.nchem > 0 ? eb::PART_FLUID : eb::PART_ALL, eb::PART_TRACERS};
+  for (int q = 0; q < (split && P.nchem > 0 ? 2 : 1); q++) {
+    const int part = parts[q];
+    const int nf = part == eb::PART_ALL ? 5 + P.nchem : (part == eb::PART_FLUID ? 5 : P.nchem);
+    eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, nf, threads, pair);
+    P.pair_sync = L.pair;
+    if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
+    P.seg_len = L.seg_len;
+    const dim3 grid(L.gx, L.gy, L.gz), block(L.tx, L.ty, 1);
+#define EMU_LAUNCH(GW, AG)                                                                                            \
+    do {                                                                                                              \
+      if (part == eb::PART_ALL) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_ALL>, grid, block, L.smem, P);      \
+      else if (part == eb::PART_FLUID) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_FLUID>, grid, block, L.smem, P); \
+      else cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_TRACERS>, grid, block, L.smem, P);                \
+    } while (0)
+    // the three instantiations launch_box() chooses from on the device
+    if (g_in_wdot) EMU_LAUNCH(true, false);
+    else if (aux_in_gen) EMU_LAUNCH(false, true);
+    else EMU_LAUNCH(false, false);
+#undef EMU_LAUNCH
+  }
   *state_bits = flag;
   return flag ? -1 : 0;
 }
@@ -62,7 +76,7 @@ extern "C" int emu_decompose(int nprocs, int rank, const int64_t* n, const int32
 
 extern "C" double emu_boundary_tile_fraction(const long* lo, const long* hi, long nx, long ny, int nchem, int threads)
 {
-  const eb::LaunchGeom L = eb::launch_geom(lo, hi, nchem, threads, 2);
+  const eb::LaunchGeom L = eb::launch_geom(lo, hi, 5 + nchem, threads, 2);
   return eb::boundary_tile_fraction(lo, hi, nx, ny, L);
 }
 

@@ -122,6 +122,50 @@ def test_emulated_forcing_taken_from_wdot(emu, oracle_mod, port, n, nchem, bcs, 
             assert np.array_equal(a, g + b)
 
 
+@pytest.mark.parametrize("n,nchem,bcs,threads,pair", [
+    ((12, 9, 7), 2, [N] * 6, 384, 0),
+    ((35, 25, 9), 10, [P, P, R, R, N, N], 384, 2),   # production tile shape, row rendezvous
+    ((70, 12, 10), 4, [P] * 6, 128, 1),              # interior CTAs reading the per-cell arrays
+    ((3, 20, 17), 3, [N] * 6, 256, 0),               # thin x, odd nchem (scalar species path)
+    ((33, 5, 26), 6, [R] * 6, 64, 0),                # several z-segments
+])
+def test_emulated_split_launches_equal_the_fused_launch(emu, oracle_mod, port, n, nchem, bcs, threads, pair):
+    """EULERB200_SPLIT: the fluid fields and the species evaluated by two launches (PART_FLUID,
+    PART_TRACERS).  The species launch rebuilds the face-local alpha and the normal velocities from the
+    per-cell arrays with the operations fluid_face uses, so the result is bit-identical to the fused
+    launch wherever both read the same per-cell values: without the arrays, and in the boundary-heavy
+    instantiation.  (In boundary tiles the default fused instantiation derives p from the sweep-ordered
+    momenta, the species launch reads the array: c and alpha can differ in the last bit there.)"""
+    w = oracle_mod.random_state(n, nchem, seed=5 + sum(n))
+    d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+    forcing = [0.1, 0, -0.1, 0, 0.3]
+    ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
+    for extra in (dict(use_aux=0), dict(aux_in_gen=1), dict()):
+        ret0, base, b0 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, pair=pair, **extra)
+        ret1, got, b1 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, pair=pair, split=1, **extra)
+        assert ret0 == 0 and ret1 == 0 and b0 == b1 == 0
+        if extra:
+            assert all(np.array_equal(a, b) for a, b in zip(base, got))
+        assert all(np.array_equal(a, b) for a, b in zip(base[:5], got[:5]))
+        assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
+    rng = np.random.default_rng(9)
+    G = [rng.normal(size=x.size) for x in base]
+    _, gw0, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads, g_in_wdot=G, use_aux=0)
+    _, gw1, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=threads, g_in_wdot=G, split=1, use_aux=0)
+    assert all(np.array_equal(a, b) for a, b in zip(gw0, gw1))
+    ws = [x.copy() for x in w]
+    ws[5].reshape(-1, nchem)[:, -1] += 2.0
+    _, s0, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, [x.copy() for x in ws], threads=threads, energy_units=3.0, aux_in_gen=1)
+    _, s1, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, [x.copy() for x in ws], threads=threads, energy_units=3.0, split=1, aux_in_gen=1)
+    assert all(np.array_equal(a, b) for a, b in zip(s0, s1))
+    # an illegal state is reported by the fluid launch
+    wb = [x.copy() for x in w]
+    wb[0][7] = -1.0
+    r0 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, wb, threads=threads)
+    r1 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, wb, threads=threads, split=1)
+    assert r0[0] == r1[0] == -1 and r0[2] == r1[2] != 0
+
+
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)
@@ -223,6 +267,7 @@ def test_emulated_random_configurations(emu, oracle_mod, port):
         threads = int(rng.choice([64, 128, 256, 384]))
         kw = dict(forcing=[0, 0.3, -0.1, 0, 0.2], threads=threads, pair=int(rng.integers(0, 3)),
                   aux_in_gen=int(rng.integers(0, 2)), use_aux=int(rng.integers(0, 2)))
+        kw["split"] = case % 2            # fluid fields and species in separate launches
         w = oracle_mod.random_state(n, nchem, seed=int(rng.integers(1, 1000)))
         d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
         ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, **kw)
@@ -299,7 +344,7 @@ def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
                 if any(bhi[a] <= blo[a] for a in range(3)):
                     continue
                 ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi,
-                                          threads=threads, aux_in_gen=ag)
+                                          threads=threads, aux_in_gen=ag, split=done % 2)
                 assert ret == 0, tag
                 for o_, p_ in zip(out, part):
                     m = ~np.isnan(p_)
