@@ -92,11 +92,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("EULERB200_LIB", LIB_PATH)      # tuning: another build of the same library
+    if not os.path.exists(path):
         raise RuntimeError(
             "%s is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
-            "There is no CPU fallback for the fluid RHS." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "There is no CPU fallback for the fluid RHS." % path)
+    lib = C.CDLL(path)
     for name, (res, args) in ABI.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res

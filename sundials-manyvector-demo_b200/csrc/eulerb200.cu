@@ -158,7 +158,7 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set[4][3][3] = {}, carveout_for[4][3][3] = {};   // per kernel instantiation [variant][kind][part]
+  size_t max_smem_set[5][3][3] = {}, carveout_for[5][3][3] = {};   // per kernel instantiation [variant][kind][part]
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
   long ctas_target = 5920;       // EULERB200_CTAS: CTAs a launch aims for when cutting z-segments (tuning)
   int force_kernel = 0;          // EULERB200_KERNEL=1: allow the AG instantiation for boundary-heavy launches
@@ -167,6 +167,9 @@ struct eulerb200_ctx {
   int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
+  double* chemT = nullptr;                                 // pair-interleaved copy of the species (RhsParams::chemT)
+  bool use_chemT = false;                                  // EULERB200_CHEMT=1: species read from the pair-interleaved copy (measured:
+                                                           // kernel -0.6 ms, pre-pass +5.4 ms at 512^3 / nchem 10, so off by default)
   int pair_sync = 2;                                       // EULERB200_PAIR: 0 CTA-wide barriers, 1/2 pairwise row rendezvous (rhs_kernel.cuh)
 };
 
@@ -184,17 +187,24 @@ struct KernelVariant {
   int threads;
   const char* name;
 };
-#define EB_K(T, B, GW, AG, PART) eb::rhs_fused_kernel<T, B, GW, AG, eb::PART>
-#define EB_KIND(T, B, GW, AG) {EB_K(T, B, GW, AG, PART_ALL), EB_K(T, B, GW, AG, PART_FLUID), EB_K(T, B, GW, AG, PART_TRACERS)}
-#define EB_KERNELS_FULL(T, B) {EB_KIND(T, B, false, false), EB_KIND(T, B, false, true), EB_KIND(T, B, true, false)}
-#define EB_KERNELS_PLAIN(T, B) {EB_KIND(T, B, false, false), {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
+#define EB_K(T, B, GW, AG, PART, TYC) eb::rhs_fused_kernel<T, B, GW, AG, eb::PART, TYC>
+#define EB_KIND(T, B, GW, AG, TYC) {EB_K(T, B, GW, AG, PART_ALL, TYC), EB_K(T, B, GW, AG, PART_FLUID, TYC), EB_K(T, B, GW, AG, PART_TRACERS, TYC)}
+#define EB_KERNELS_FULL(T, B, TYC) {EB_KIND(T, B, false, false, TYC), EB_KIND(T, B, false, true, TYC), EB_KIND(T, B, true, false, TYC)}
+#define EB_KERNELS_PLAIN(T, B, TYC) {EB_KIND(T, B, false, false, TYC), {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
+// [0..3]: CTAs of 32 x threads/32 threads, tile shape compiled in; [4]: any tile shape of up to 384
+// threads (thin or small boxes, many species), shape read from blockDim
+#ifdef EB_FAST_BUILD      // tuning builds: default kind only
+#define EB_KERNELS_FULL EB_KERNELS_PLAIN
+#endif
 const KernelVariant kVariants[] = {
-    {EB_KERNELS_PLAIN(256, 1), 256, "256x1 (<=255 regs)"},
-    {EB_KERNELS_FULL(384, 1), 384, "384x1 (<=168 regs)"},
-    {EB_KERNELS_FULL(512, 1), 512, "512x1 (<=128 regs)"},
-    {EB_KERNELS_PLAIN(640, 1), 640, "640x1 (<=96 regs)"},
+    {EB_KERNELS_PLAIN(256, 1, 8), 256, "256x1 (<=255 regs)"},
+    {EB_KERNELS_FULL(384, 1, 12), 384, "384x1 (<=168 regs)"},
+    {EB_KERNELS_FULL(512, 1, 16), 512, "512x1 (<=128 regs)"},
+    {EB_KERNELS_PLAIN(640, 1, 20), 640, "640x1 (<=96 regs)"},
+    {EB_KERNELS_FULL(384, 1, 0), 384, "any tile shape, <= 384 threads"},
 };
-const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+const int kGenericVariant = 4;
+const int kNumVariants = 4;    // selectable; the last entry is the any-shape fallback
 const int kDefaultVariant = 1;
 
 int fail(eulerb200_ctx* c, int code, const std::string& msg)
@@ -230,7 +240,9 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
     eb::ghost_face(g, f, c->recv_cur[f], &P.ghost[f]);
   }
   for (int q = 0; q < 4; q++) P.aux[q] = c->use_aux ? c->aux[q] : nullptr;
+  P.chemT = (c->use_chemT && g.nchem > 0) ? c->chemT : nullptr;
   P.slow_mode = 0;
+  P.vec_store = (g.nchem > 0 && (g.nchem & 1) == 0 && (((unsigned long long)wdot[5]) & 15ull) == 0ull) ? 1 : 0;
   P.pair_sync = 0;
   P.inv_energy_units = 1.0;
   P.et_rw = nullptr;
@@ -246,10 +258,16 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
 int launch_part(eulerb200_ctx* c, eb::RhsParams P, int kind, int part, cudaStream_t s)
 {
   const int nf = part == eb::PART_ALL ? 5 + P.nchem : (part == eb::PART_FLUID ? 5 : P.nchem);
-  const int vi = c->variant_part[part];
+  int vi = c->variant_part[part];
+  eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, nf, kVariants[vi].threads, c->pair_sync, c->ctas_target);
+  if (L.tx != 32 || L.ty != kVariants[vi].threads / 32 || !kVariants[vi].fn[kind][part]) {
+    // not the compiled-in tile shape (thin or small box, many species), or a kind compiled for the
+    // default variant only: the any-shape instantiation
+    vi = kGenericVariant;
+    L = eb::launch_geom(P.lo, P.hi, nf, kVariants[vi].threads, c->pair_sync, c->ctas_target);
+  }
   const KernelVariant& V = kVariants[vi];
   void (*const fn)(const eb::RhsParams) = V.fn[kind][part];
-  const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, nf, V.threads, c->pair_sync, c->ctas_target);
   P.seg_len = L.seg_len;
   P.pair_sync = L.pair;
   size_t& smem_set = c->max_smem_set[vi][kind][part];
@@ -286,23 +304,29 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
     const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, 5 + P.nchem, kVariants[c->variant_part[0]].threads, c->pair_sync, c->ctas_target);
     if (eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) kind = 1;
   }
-  const bool split = c->split && P.nchem > 0 && kVariants[c->variant_part[1]].fn[kind][1] && kVariants[c->variant_part[2]].fn[kind][2];
-  if (split) {
-    int rc = launch_part(c, P, kind, eb::PART_FLUID, s);
-    if (rc) return rc;
-    return launch_part(c, P, kind, eb::PART_TRACERS, s);
+  int rc;
+  if (c->split && P.nchem > 0) {
+    rc = launch_part(c, P, kind, eb::PART_FLUID, s);
+    if (!rc) rc = launch_part(c, P, kind, eb::PART_TRACERS, s);
+  } else {
+    rc = launch_part(c, P, kind, eb::PART_ALL, s);
   }
-  if (!kVariants[c->variant_part[0]].fn[kind][0]) c->variant_part[0] = kDefaultVariant;   // kind compiled for the default only
-  return launch_part(c, P, kind, eb::PART_ALL, s);
+  if (rc || !P.slow_mode) return rc;
+  // fslow / fexpl: etdot moves into the gas-energy species of this box
+  const long ncell = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+  eb::slow_post_kernel<<<(unsigned)std::min<long>((ncell + 255) / 256, 148L * 16), 256, 0, s>>>(P);
+  c->launches++;
+  EB_CUDA(c, cudaGetLastError());
+  return 0;
 }
 
 // Per-cell derived values for the z-planes [k0, k1) of the state in P.
 int launch_aux(eulerb200_ctx* c, const eb::RhsParams& P, long k0, long k1, cudaStream_t s)
 {
-  if ((!c->use_aux && !P.slow_mode) || k1 <= k0) return 0;
+  if ((!c->use_aux && !P.slow_mode && !P.chemT) || k1 <= k0) return 0;
   const long plane = P.nx * P.ny, c0 = k0 * plane, c1 = k1 * plane;
   const unsigned blocks = (unsigned)std::min<long>((c1 - c0 + 255) / 256, 148L * 16);
-  eb::aux_kernel<<<blocks, 256, 0, s>>>(P, c->aux[0], c->aux[1], c->aux[2], c->aux[3], c0, c1);
+  eb::aux_kernel<<<blocks, 256, 0, s>>>(P, c->aux[0], c->aux[1], c->aux[2], c->aux[3], const_cast<double*>(P.chemT), c0, c1);
   c->launches++;
   EB_CUDA(c, cudaGetLastError());
   return 0;
@@ -444,6 +468,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   *out = nullptr;
   if (cfg->nxl < 3 || cfg->nyl < 3 || cfg->nzl < 3) return fail(nullptr, -1, "local extents must be >= 3 (euler3D.hpp:483-494)");
   if (cfg->nchem < 0 || 5 + cfg->nchem > 64) return fail(nullptr, -1, "nchem out of range");
+  if ((double)cfg->nxl * (double)cfg->nyl * (double)cfg->nzl >= 2147483648.0) return fail(nullptr, -1, "more than 2^31 - 1 cells per rank");
   if (!(cfg->dx > 0) || !(cfg->dy > 0) || !(cfg->dz > 0)) return fail(nullptr, -1, "mesh spacing must be positive");
   for (int f = 0; f < 6; f++) {
     eb::GhostFace g;
@@ -466,7 +491,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_VARIANT_F")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[1] = v; }
   if (const char* ev = getenv("EULERB200_VARIANT_T")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[2] = v; }
   if (const char* ev = getenv("EULERB200_SPLIT")) c->split = atoi(ev) != 0;
-  for (int a_ = 0; a_ < 4; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
+  for (int a_ = 0; a_ < 5; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
   if (cfg->device >= 0) {
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
@@ -490,9 +515,12 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
   if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) == 1) ? 1 : 0;
   if (const char* ev = getenv("EULERB200_CTAS")) c->ctas_target = std::max(1L, atol(ev));
+  if (const char* ev = getenv("EULERB200_CHEMT")) c->use_chemT = (atoi(ev) != 0);
   if (c->use_aux)
     for (int q = 0; q < 4; q++)
       EB_CREATE(cudaMalloc(&c->aux[q], sizeof(double) * cfg->nxl * cfg->nyl * cfg->nzl));
+  if (c->use_chemT && cfg->nchem > 0)
+    EB_CREATE(cudaMalloc(&c->chemT, sizeof(double) * 2 * ((cfg->nchem + 1) / 2) * cfg->nxl * cfg->nyl * cfg->nzl));
   for (int f = 0; f < 6; f++) {
     c->remote[f] = eb::face_is_remote(*cfg, f);
     if (c->remote[f]) {
@@ -544,6 +572,7 @@ int eulerb200_destroy(eulerb200_ctx* c)
     if (c->ev_join[h]) cudaEventDestroy(c->ev_join[h]);
   }
   for (int q = 0; q < 4; q++) if (c->aux[q]) cudaFree(c->aux[q]);
+  if (c->chemT) cudaFree(c->chemT);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->d_alpha) cudaFree(c->d_alpha);

@@ -29,6 +29,13 @@
 #pragma once
 #include "euler_math.cuh"
 
+// EB_ABLATE: bit mask of measurement-only ablations used by tools/ablate.cu to attribute kernel time
+// (1 no barriers, 2 species values synthesised instead of loaded, 4 results not stored, 8 the
+// species launch's u and c synthesised instead of loaded).  Never defined in the product build.
+#ifndef EB_ABLATE
+#define EB_ABLATE 0
+#endif
+
 namespace eb {
 
 enum { GHOST_MAP = 0, GHOST_BUF = 1 };
@@ -61,13 +68,19 @@ struct RhsParams {
   GhostFace ghost[6];       // W,E,S,N,B,F
   const double* aux[4];     // per-cell 1/rho, p, c, sqrt(rho) from aux_kernel (or all NULL:
                             // everything derived on the fly)
+  const double* chemT;      // pair-interleaved copy of the species made by aux_kernel (or NULL):
+                            // species 2q, 2q+1 of cell c at chemT[2 (q N + c)], N = nx ny nz.  The
+                            // vector the drivers own is species-fastest (euler3D.hpp:65): a warp
+                            // reading one species pair of 32 neighbouring cells from it touches 20
+                            // cache lines (stride 80 B at nchem = 10), from this copy 4-5.
   int* state_flag;          // OR of legal_state failure bits (euler3D.hpp:1405-1414)
   // "slow RHS" mode of the multirate / IMEX drivers (fslow, multirate_chem_hydro_main.cpp:
   // 996-1083; fexpl, imex_chem_hydro_main.cpp:910-1000): before the fluxes the total energy is
   // rebuilt from the gas energy carried as the LAST chemistry species,
-  //   et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho)            (:1033-1042, written into w)
-  // and afterwards  chemdot[nchem-1] = etdot,  etdot = 0        (:1059-1068).
+  //   et = chem[nchem-1]/EnergyUnits + |m|^2/(2 rho)            (:1033-1042, written into w by aux_kernel)
+  // and afterwards  chemdot[nchem-1] = etdot,  etdot = 0        (:1059-1068, slow_post_kernel).
   int pair_sync;                      // rows of the tile rendezvous pairwise (see rhs_fused_kernel)
+  int vec_store;                      // species pairs go out as one 16-byte store (nchem even, wdot[5] 16-byte aligned)
   int slow_mode;
   double inv_energy_units;
   double* et_rw;            // w[4] again, writable, for the rebuild (slow mode only)
@@ -78,7 +91,8 @@ struct RhsParams {
 
 // One resolved stencil point: where to read it and which fields change sign.
 struct StencilPt {
-  long off;        // owned: cell index; halo buffer: index of field 0
+  unsigned off;    // owned: cell index; halo buffer: index of field 0.  32 bits on purpose: one
+                   // IMAD.WIDE forms base + 8 off (eulerb200_create refuses boxes of 2^31 cells or more)
   unsigned neg;
   int src;         // -1 owned, else face id of the halo buffer
 };
@@ -94,7 +108,7 @@ EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilP
 #pragma unroll
   for (int l = 0; l < 6; l++) {
     const long pos = idx - 3 + l;
-    pt[l].off = cell + (l - 3) * stride;
+    pt[l].off = (unsigned)(cell + (l - 3) * stride);
     pt[l].neg = 0u;
     pt[l].src = -1;
     if (GEN) {
@@ -104,14 +118,14 @@ EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilP
         const GhostFace& G = P.ghost[f];
         if (G.mode == GHOST_MAP) {
           const long mapped = G.a + (long)G.b * pos;
-          pt[l].off = cell + (mapped - idx) * stride;
+          pt[l].off = (unsigned)(cell + (mapped - idx) * stride);
           pt[l].neg = G.neg;
         } else {
           const long d = (pos < 0) ? pos + 3 : pos - n;
           const long ta = (dir == 0) ? j : i;
           const long tb = (dir == 2) ? j : k;
           const long na = (dir == 0) ? P.ny : P.nx;
-          pt[l].off = (long)(5 + P.nchem) * (d + 3 * (ta + na * tb));
+          pt[l].off = (unsigned)((long)(5 + P.nchem) * (d + 3 * (ta + na * tb)));
           pt[l].src = f;
         }
       }
@@ -125,15 +139,27 @@ EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilP
 EB_HD void st_out(double* p, double x)
 {
 #if defined(__CUDA_ARCH__)
+  if (EB_ABLATE & 4) { if (x == 1.234567e300) *p = x; return; }
   __stcs(p, x);
 #else
   *p = x;
 #endif
 }
 
+EB_HD void st_out2(double* p, double x, double y)      // p 16-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+  if (EB_ABLATE & 4) { if (x == 1.234567e300) *p = y; return; }
+  __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));
+#else
+  p[0] = x; p[1] = y;
+#endif
+}
+
 template <bool GEN>
 EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
 {
+  if (EB_ABLATE & 16) return (field == 0 || field == 4) ? 1.5 + 1e-9 * (double)pt.off : 0.1 + 1e-9 * (double)(pt.off + field);
   if (GEN) {
     double x = (pt.src < 0) ? P.w[field][pt.off] : P.ghost[pt.src].buf[pt.off + field];
     return ((pt.neg >> field) & 1u) ? -x : x;
@@ -148,6 +174,7 @@ EB_HD double load_fluid(const RhsParams& P, const StencilPt& pt, int field)
 template <bool GEN>
 EB_HD void point_uc(const RhsParams& P, const StencilPt& pt, int fn, int f1, int f2, double& u, double& c)
 {
+  if (EB_ABLATE & 8) { u = 0.1 + 1e-9 * (double)pt.off; c = 1.0 + 1e-10 * (double)pt.off; return; }
   const bool owned = !GEN || pt.src < 0;
   if (P.aux[0] != nullptr && owned && (!GEN || (pt.neg & 0x11u) == 0u)) {
     u = load_fluid<GEN>(P, pt, fn) * P.aux[0][pt.off];
@@ -190,7 +217,12 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     }
     // Per-cell derived values: interior CTAs read what aux_kernel stored; CTAs that touch
     // ghost or halo points derive them from the (sign-mapped) state they just loaded.
-    if (!GEN && P.aux[0] != nullptr) {
+    if (EB_ABLATE & 16) {
+#pragma unroll
+      for (int l = 0; l < 6; l++) { s.rinv[l] = 0.6 + 1e-9 * (double)pt[l].off; s.p[l] = 0.9 + 1e-9 * (double)pt[l].off; s.c[l] = 1.0 + 1e-9 * (double)pt[l].off; }
+      s.srL = 1.2 + 1e-9 * (double)pt[2].off;
+      s.srR = 1.2 + 1e-9 * (double)pt[3].off;
+    } else if (!GEN && P.aux[0] != nullptr) {
 #pragma unroll
       for (int l = 0; l < 6; l++) {
         s.rinv[l] = P.aux[0][pt[l].off];
@@ -249,35 +281,53 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
     double up[6], um[6];
 #pragma unroll
     for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
-    // per-point base pointer (and sign) of the tracer block of the cell
-    const double* cp[6];
+    // sign of the species values of each point (Dirichlet ghosts negate them)
     double sg[6];
+    bool owned = true;         // no point of this stencil lies in a halo slab
 #pragma unroll
     for (int l = 0; l < 6; l++) {
-      if (GEN && pt[l].src >= 0) cp[l] = P.ghost[pt[l].src].buf + pt[l].off + 5;
-      else cp[l] = P.w[5] + pt[l].off * P.nchem;
       sg[l] = (GEN && ((pt[l].neg >> 5) & 1u)) ? -1.0 : 1.0;
+      if (GEN) owned = owned && (pt[l].src < 0);
     }
-    // Tracers two at a time: one 16-byte load per stencil point feeds two independent
-    // reconstructions (four WENO chains in flight), and the next pair is loaded while the
-    // current one is reconstructed.  Needs nchem even and 16-byte aligned blocks, which
-    // holds for the owned array (species-fastest, base from cudaMalloc) whenever nchem is
-    // even; halo buffers hold NVAR = 5+nchem values per cell, so their tracer block is
-    // only 8-byte aligned and takes the scalar path.
-    bool vec = ((P.nchem & 1) == 0) && ((((unsigned long long)P.w[5]) & 15ull) == 0ull);
-    if (GEN) {
+    // Species two at a time from the pair-interleaved copy: one coalesced 16-byte load per stencil
+    // point feeds two independent reconstructions (four WENO chains in flight), and the next pair
+    // is loaded while the current one is reconstructed.  Stencils that reach into a halo slab
+    // (reference wire layout, NVAR values per cell) take the scalar path below, as does a launch
+    // without the copy.
+    // 16-byte loads of species pairs: from the pair-interleaved copy (chemT), or from the vector
+    // itself when nchem is even and its base 16-byte aligned (pair q of cell c is then the double2
+    // number c nchem/2 + q)
+    const bool vec_aos = P.chemT == nullptr && (P.nchem & 1) == 0 && (((unsigned long long)P.w[5]) & 15ull) == 0ull;
+    if ((P.chemT != nullptr || vec_aos) && owned) {
+      const long N = P.nx * P.ny * P.nz;
+      const int npf = P.nchem / 2;              // full pairs; an odd species count leaves one behind
+      // pair q of stencil point l is at qb[io[l]]: one 64-bit base for all six points, advanced once
+      // per pair, and 32-bit offsets (one IMAD.WIDE per load)
+      const double2* qb = reinterpret_cast<const double2*>(vec_aos ? P.w[5] : P.chemT);
+      const unsigned istride = vec_aos ? (unsigned)npf : 1u;
+      const long qstep = vec_aos ? 1 : N;
+      unsigned io[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++) vec = vec && (pt[l].src < 0);
-    }
-    if (vec) {
+      for (int l = 0; l < 6; l++) io[l] = pt[l].off * istride;
+      // Slots 0 .. npf-1 hold two species, slot npf (odd nchem, chemT only) one.  The next slot is
+      // loaded while the current one is reconstructed; the loop body is branch-free on purpose (the
+      // last iteration re-loads its own slot: a conditional load here makes ptxas spill ~4 KB).
+      const int ns = npf + (P.nchem & 1);
       double2 c[6], cn[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++) c[l] = *reinterpret_cast<const double2*>(cp[l]);
+      for (int l = 0; l < 6; l++) {
+        if (EB_ABLATE & 2) { c[l].x = up[l] * 1.25 + (double)pt[l].off * 1e-9; c[l].y = um[l] * 0.75; }
+        else c[l] = qb[io[l]];
+      }
+      emit.species_begin();
 #pragma unroll 1
-      for (int v = 0; v < P.nchem; v += 2) {
-        const int vn = (v + 2 < P.nchem) ? v + 2 : v;
+      for (int q = 0; q < ns; q++) {
+        qb += (q + 1 < ns) ? qstep : 0;
 #pragma unroll
-        for (int l = 0; l < 6; l++) cn[l] = *reinterpret_cast<const double2*>(cp[l] + vn);
+        for (int l = 0; l < 6; l++) {
+          if (EB_ABLATE & 2) { cn[l].x = c[l].y * 1.0625 + (double)q; cn[l].y = c[l].x * 0.9375; }
+          else cn[l] = qb[io[l]];
+        }
         double a[6], b[6];
 #pragma unroll
         for (int l = 0; l < 6; l++) {
@@ -286,12 +336,17 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
         }
         const double fa = tracer_face(a, up, um);
         const double fb = tracer_face(b, up, um);
-        emit(5 + v, fa);
-        emit(6 + v, fb);
+        emit.pair_next(fa, fb, q < npf);
 #pragma unroll
         for (int l = 0; l < 6; l++) c[l] = cn[l];
       }
     } else {
+      const double* cp[6];
+#pragma unroll
+      for (int l = 0; l < 6; l++) {
+        if (GEN && pt[l].src >= 0) cp[l] = P.ghost[pt[l].src].buf + pt[l].off + 5;
+        else cp[l] = P.w[5] + (long)pt[l].off * P.nchem;
+      }
 #pragma unroll 1
       for (int v = 0; v < P.nchem; v++) {
         double c[6];
@@ -310,14 +365,92 @@ EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, l
   return gen ? face_all<true, AG, PART>(P, dir, i, j, k, emit) : face_all<false, AG, PART>(P, dir, i, j, k, emit);
 }
 
+// What face_all hands its fluxes to.  Fluid fields: emit(v, flux).  Species, in order and two at a
+// time: emit.species_begin(), then emit.pair_next(fa, fb, two) per pair (two == false: the odd one
+// out) -- the emitter keeps running pointers, so that the species loop carries no index
+// arithmetic (on B200 an integer instruction next to the DFMA stream is not free, profiles/README.md).
+// Array strides are compile-time constants in the instantiations with a fixed tile shape (S > 0).
+// (1) into the shared-memory slot of the field (FX / FY / ZLO of rhs_fused_kernel)
+template <int S>
+struct EmitSlot {
+  double* base;
+  int rs;              // run-time stride (S == 0)
+  double* sp;
+  EB_HD int stride() const { return S > 0 ? S : rs; }
+  EB_HD void operator()(int v, double x) const { base[v * stride()] = x; }
+  EB_HD void species_begin() { sp = base + 5 * stride(); }
+  EB_HD void pair_next(double a, double b, bool two) { sp[0] = a; if (two) sp[stride()] = b; sp += 2 * stride(); }
+};
+// (2) the flux through the z-face above the cell closes the divergence of its field (sum order of
+// utilities.cpp:202-207) and the result goes out to wdot; a species pair as one 16-byte store
+template <bool GW, int TRc, int Tc>
+struct EmitDiv {
+  const RhsParams& P;
+  double* FX;
+  double* FY;
+  double* ZLO;
+  int rTR, rT, TX;
+  long cell;
+  double *fx, *fy, *zl, *dst;    // running pointers of the species part
+  bool fast;                     // species pairs: plain 16-byte stores
+  EB_HD int TR() const { return TRc > 0 ? TRc : rTR; }
+  EB_HD int T() const { return Tc > 0 ? Tc : rT; }
+  EB_HD double close(int v, double zup) const
+  {
+    const double div = ((FX[v * TR() + 1] - FX[v * TR()]) * P.rdx + (FY[v * T() + TX] - FY[v * T()]) * P.rdy)
+                       + (zup - ZLO[v * TR()]) * P.rdz;
+    ZLO[v * TR()] = zup;
+    return div;
+  }
+  EB_HD void store(int v, double div) const
+  {
+    double* d = (v < 5) ? P.wdot[v] + cell : P.wdot[5] + cell * P.nchem + (v - 5);
+    // GW: the caller ran external_forces itself, wdot already holds G (utilities.cpp:65)
+    st_out(d, (GW ? *d : (v < 5 ? P.forcing[v] : 0.0)) - div);
+  }
+  EB_HD void operator()(int v, double zup) const { store(v, close(v, zup)); }
+  EB_HD void species_begin()
+  {
+    fx = FX + 5 * TR(); fy = FY + 5 * T(); zl = ZLO + 5 * TR();
+    dst = P.wdot[5] + cell * P.nchem;
+    fast = !GW && P.vec_store;
+  }
+  EB_HD double close_next(int q, double zup) const      // q-th species (0 / 1) at the running pointers
+  {
+    return ((fx[q * TR() + 1] - fx[q * TR()]) * P.rdx + (fy[q * T() + TX] - fy[q * T()]) * P.rdy)
+           + (zup - zl[q * TR()]) * P.rdz;
+  }
+  EB_HD void pair_next(double za, double zb, bool two)    // two == false: the odd species out, zb unused
+  {
+    const double da = close_next(0, za);
+    zl[0] = za;
+    if (fast) {                         // (nchem even: always two)
+      const double db = close_next(1, zb);
+      zl[TR()] = zb;
+      st_out2(dst, 0.0 - da, 0.0 - db);
+    } else {
+      st_out(dst, (GW ? dst[0] : 0.0) - da);
+      if (two) {
+        const double db = close_next(1, zb);
+        zl[TR()] = zb;
+        st_out(dst + 1, (GW ? dst[1] : 0.0) - db);
+      }
+    }
+    fx += 2 * TR(); fy += 2 * T(); zl += 2 * TR(); dst += 2;
+  }
+};
+
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
 
-// Pre-pass: per-cell 1/rho, p, c, sqrt(rho) for the cells [c0, c1) (40 B read, 32 B written
-// per cell), so that the 18 stencils a cell sits in do not each redo a reciprocal and two
-// square roots on the FP64 pipe.
-__global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2, double* a3, long c0, long c1)
+// Pre-pass over the cells [c0, c1): per-cell 1/rho, p, c, sqrt(rho) (40 B read, 32 B written per
+// cell), so that the 18 stencils a cell sits in do not each redo a reciprocal and two square roots on
+// the FP64 pipe; and the pair-interleaved copy of the species (8 nchem B read and written per cell;
+// see RhsParams::chemT), read with one thread per 16-byte chunk so that both sides stay coalesced.
+__global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2, double* a3, double* chemT,
+                           long c0, long c1)
 {
-  for (long c = c0 + (long)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (long)gridDim.x * blockDim.x) {
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+  for (long c = c0 + tid; c < c1; c += nthr) {
     const double r = P.w[0][c], mx = P.w[1][c], my = P.w[2][c], mz = P.w[3][c];
     double e = P.w[4][c];
     if (P.slow_mode) {
@@ -328,6 +461,48 @@ __global__ void aux_kernel(const RhsParams P, double* a0, double* a1, double* a2
       const CellAux a = cell_aux(P.gamma, r, mx, my, mz, e);
       a0[c] = a.rinv; a1[c] = a.p; a2[c] = a.c; a3[c] = a.sr;
     }
+  }
+  if (chemT != nullptr && P.nchem > 0) {
+    // blocks of 256 cells per CTA; chunk j of a block is species pair j % np of its cell j / np
+    // (32-bit arithmetic: a 64-bit division per chunk would cost as much as the copy itself)
+    const long N = P.nx * P.ny * P.nz;
+    const unsigned np = (unsigned)(P.nchem + 1) / 2u;
+    const bool vec = (P.nchem & 1) == 0 && (((unsigned long long)P.w[5]) & 15ull) == 0ull;
+    const double2* src2 = reinterpret_cast<const double2*>(P.w[5]);
+    double2* dst2 = reinterpret_cast<double2*>(chemT);
+    const long nblk = (c1 - c0 + 255) / 256;
+    for (long b = blockIdx.x; b < nblk; b += gridDim.x) {
+      const long cb = c0 + b * 256;
+      const unsigned ncb = (unsigned)((c1 - cb < 256) ? c1 - cb : 256);
+      for (unsigned j = threadIdx.x; j < ncb * np; j += blockDim.x) {
+        const unsigned cl = j / np, h = j - cl * np;
+        const long c = cb + cl;
+        if (vec) {
+          dst2[(long)h * N + c] = src2[cb * np + j];
+        } else {
+          double2 x;
+          x.x = P.w[5][c * P.nchem + 2 * h];
+          x.y = (2 * (int)h + 1 < P.nchem) ? P.w[5][c * P.nchem + 2 * h + 1] : 0.0;
+          dst2[(long)h * N + c] = x;
+        }
+      }
+    }
+  }
+}
+
+// fslow / fexpl post-step (multirate_chem_hydro_main.cpp:1059-1068, imex_chem_hydro_main.cpp fexpl):
+// chemdot[nchem-1] = etdot, etdot = 0 for the cells of the box [P.lo, P.hi) -- 8 B read, 16 B written
+// per cell, on the device (the reference copies the whole chemistry vector to the host and back
+// around fEuler in its GPU builds, :1028-1031,1070-1073).
+__global__ void slow_post_kernel(const RhsParams P)
+{
+  const long ex = P.hi[0] - P.lo[0], ey = P.hi[1] - P.lo[1], ez = P.hi[2] - P.lo[2];
+  const long n = ex * ey * ez;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    const long k = q / (ex * ey), r = q - k * ex * ey, j = r / ex, i = r - j * ex;
+    const long c = (P.lo[0] + i) + P.nx * ((P.lo[1] + j) + P.ny * (P.lo[2] + k));
+    P.wdot[5][c * P.nchem + (P.nchem - 1)] = P.wdot[4][c];
+    P.wdot[4][c] = 0.0;
   }
 }
 
@@ -359,11 +534,14 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // external_forces hook into wdot (utilities.cpp:65) and every store is wdot = wdot - div.
 // AG: boundary tiles read the per-cell arrays wherever they are valid (see face_all).
 // PART: all fields, or the fluid fields / the species only (two launches, see the enum).
-template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL>
+// TYC: 0, or the number of tile rows of a launch whose CTAs are 32 x TYC threads (tile shape and
+// shared-memory strides are then compile-time constants).
+template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL, int TYC = 0>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
-  const int TX = blockDim.x, TY = blockDim.y, T = TX * TY;
+  const int TX = TYC > 0 ? 32 : (int)blockDim.x, TY = TYC > 0 ? TYC : (int)blockDim.y, T = TX * TY;
+  constexpr int Tc = 32 * TYC, TRc = TYC > 0 ? 32 * (TYC - 1) : 0;
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
   // fields of this launch: v0 .. v0+nf-1 in the reference's order
   const int v0 = (PART == PART_TRACERS) ? 5 : 0;
@@ -397,18 +575,18 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
   // z-face below the first plane of the segment
   if (owns)
-    face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0,
-                  [&](int v, double x) { ZLO[v * TR] = x; });
+    face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0, EmitSlot<TRc>{ZLO, TR, nullptr});
 
   for (long k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (need_x) {
-      const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, [&](int v, double x) { FX[v * TR] = x; });
+      const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, EmitSlot<TRc>{FX, TR, nullptr});
       if (owns) mask |= bits;
     }
     if (need_y)
-      face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, [&](int v, double x) { FY[v * T] = x; });
-    if (pair) {
+      face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr});
+    if (EB_ABLATE & 1) {
+    } else if (pair) {
       if (ty > 0) eb_bar_sync(ty, 64);
       if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
     } else {
@@ -420,37 +598,10 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     if (owns) {
       const long cell = i + P.nx * (j + P.ny * k);
       face_dispatch<AG, PART>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
-                    [&](int v, double zup) {
-                      const double div = ((FX[v * TR + 1] - FX[v * TR]) * P.rdx
-                                        + (FY[v * T + TX] - FY[v * T]) * P.rdy)
-                                        + (zup - ZLO[v * TR]) * P.rdz;
-                      ZLO[v * TR] = zup;
-                      if (GW) {
-                        // the caller ran external_forces itself: wdot already holds G (utilities.cpp:65)
-                        double* dst = (v < 5) ? P.wdot[v] + cell : P.wdot[5] + cell * P.nchem + (v - 5);
-                        const double G = *dst;
-                        if (!P.slow_mode) {
-                          st_out(dst, G - div);
-                        } else if (v == 4) {
-                          st_out(P.wdot[5] + cell * P.nchem + (P.nchem - 1), G - div);
-                          st_out(dst, 0.0);
-                        } else if (v < 4 + P.nchem) {
-                          st_out(dst, G - div);
-                        }
-                      } else if (!P.slow_mode) {
-                        if (v < 5) st_out(P.wdot[v] + cell, P.forcing[v] - div);
-                        else st_out(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
-                      } else if (v == 4) {          // etdot goes to the gas-energy species
-                        st_out(P.wdot[5] + cell * P.nchem + (P.nchem - 1), P.forcing[4] - div);
-                        st_out(P.wdot[4] + cell, 0.0);
-                      } else if (v < 4) {
-                        st_out(P.wdot[v] + cell, P.forcing[v] - div);
-                      } else if (v < 4 + P.nchem) {  // every species but the last (overwritten above)
-                        st_out(P.wdot[5] + cell * P.nchem + (v - 5), 0.0 - div);
-                      }
-                    });
+                              EmitDiv<GW, TRc, Tc>{P, FX, FY, ZLO, TR, T, TX, cell, nullptr, nullptr, nullptr, nullptr, false});
     }
-    if (two_fy) {
+    if (EB_ABLATE & 1) {
+    } else if (two_fy) {
       __syncwarp();                 // FX of this plane consumed before the warp overwrites it
       FY += fy_flip;
       fy_flip = -fy_flip;

@@ -10,7 +10,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split)
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -23,19 +23,26 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   for (int f = 0; f < 6; f++)
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &P.ghost[f]) != 0) return -1;
   for (int q = 0; q < 4; q++) P.aux[q] = nullptr;
+  P.chemT = nullptr;
+  std::vector<double> chemT;
   P.slow_mode = 0; P.inv_energy_units = 1.0; P.et_rw = nullptr;
+  P.vec_store = (cfg->nchem > 0 && (cfg->nchem & 1) == 0 && (((unsigned long long)wdot[5]) & 15ull) == 0ull) ? 1 : 0;
   if (energy_units > 0.0) {        // fslow mode: aux_kernel rebuilds the total energy in w[4]
     P.slow_mode = 1;
     P.inv_energy_units = 1.0 / energy_units;
     P.et_rw = const_cast<double*>(w[4]);
   }
-  if (use_aux || P.slow_mode) {    // the product's own pre-pass kernel, launched like launch_aux() launches it
+  if (use_chemT && P.nchem > 0) {
+    chemT.assign((size_t)2 * ((P.nchem + 1) / 2) * P.nx * P.ny * P.nz, 0.0 / 0.0);
+    P.chemT = chemT.data();
+  }
+  if (use_aux || P.slow_mode || P.chemT) {    // the product's own pre-pass kernel, launched like launch_aux() launches it
     const long N = P.nx * P.ny * P.nz;
     if (use_aux) for (int q = 0; q < 4; q++) aux[q].assign(N, 0.0 / 0.0);
     double* a[4] = {nullptr, nullptr, nullptr, nullptr};
     if (use_aux) for (int q = 0; q < 4; q++) a[q] = aux[q].data();
     cuda_emu::launch_plain(eb::aux_kernel, dim3((unsigned)std::min<long>((N + 255) / 256, 148L * 16)), dim3(256), P,
-                           a[0], a[1], a[2], a[3], 0L, N);
+                           a[0], a[1], a[2], a[3], const_cast<double*>(P.chemT), 0L, N);
     if (use_aux) for (int q = 0; q < 4; q++) P.aux[q] = aux[q].data();
   }
   int flag = 0;
@@ -52,18 +59,28 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
     if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
     P.seg_len = L.seg_len;
     const dim3 grid(L.gx, L.gy, L.gz), block(L.tx, L.ty, 1);
+#define EMU_PARTS(GW, AG, TYC)                                                                                         \
+    do {                                                                                                              \
+      if (part == eb::PART_ALL) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_ALL, TYC>, grid, block, L.smem, P);      \
+      else if (part == eb::PART_FLUID) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_FLUID, TYC>, grid, block, L.smem, P); \
+      else cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_TRACERS, TYC>, grid, block, L.smem, P);                \
+    } while (0)
+    // like launch_part(): the instantiation with the tile shape compiled in where there is one (here
+    // 32 x 4 and 32 x 12), else the any-shape one
 #define EMU_LAUNCH(GW, AG)                                                                                            \
     do {                                                                                                              \
-      if (part == eb::PART_ALL) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_ALL>, grid, block, L.smem, P);      \
-      else if (part == eb::PART_FLUID) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_FLUID>, grid, block, L.smem, P); \
-      else cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_TRACERS>, grid, block, L.smem, P);                \
+      if (L.tx == 32 && L.ty == 12) EMU_PARTS(GW, AG, 12);                                                            \
+      else if (L.tx == 32 && L.ty == 4) EMU_PARTS(GW, AG, 4);                                                         \
+      else EMU_PARTS(GW, AG, 0);                                                                                      \
     } while (0)
     // the three instantiations launch_box() chooses from on the device
     if (g_in_wdot) EMU_LAUNCH(true, false);
     else if (aux_in_gen) EMU_LAUNCH(false, true);
     else EMU_LAUNCH(false, false);
 #undef EMU_LAUNCH
+#undef EMU_PARTS
   }
+  if (P.slow_mode) cuda_emu::launch_plain(eb::slow_post_kernel, dim3(3), dim3(64), P);   // as launch_box() does
   *state_bits = flag;
   return flag ? -1 : 0;
 }

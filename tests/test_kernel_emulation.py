@@ -140,7 +140,7 @@ def test_emulated_split_launches_equal_the_fused_launch(emu, oracle_mod, port, n
     d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
     forcing = [0.1, 0, -0.1, 0, 0.3]
     ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
-    for extra in (dict(use_aux=0), dict(aux_in_gen=1), dict()):
+    for extra in (dict(use_aux=0), dict(aux_in_gen=1), dict(aux_in_gen=1, chemT=0), dict()):
         ret0, base, b0 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, pair=pair, **extra)
         ret1, got, b1 = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, pair=pair, split=1, **extra)
         assert ret0 == 0 and ret1 == 0 and b0 == b1 == 0
@@ -268,6 +268,7 @@ def test_emulated_random_configurations(emu, oracle_mod, port):
         kw = dict(forcing=[0, 0.3, -0.1, 0, 0.2], threads=threads, pair=int(rng.integers(0, 3)),
                   aux_in_gen=int(rng.integers(0, 2)), use_aux=int(rng.integers(0, 2)))
         kw["split"] = case % 2            # fluid fields and species in separate launches
+        kw["chemT"] = (case // 2) % 2     # species read from the pair-interleaved copy / from the vector itself
         w = oracle_mod.random_state(n, nchem, seed=int(rng.integers(1, 1000)))
         d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
         ret, got, bits = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, **kw)
@@ -344,7 +345,7 @@ def test_emulated_random_decompositions(emu, pkg, oracle_mod, port):
                 if any(bhi[a] <= blo[a] for a in range(3)):
                     continue
                 ret, part, bits = emu.rhs(nl, nchem, d, 1.4, bcs, b["nbr"], rank, b["parts"], recv=recv, lo=blo, hi=bhi,
-                                          threads=threads, aux_in_gen=ag, split=done % 2)
+                                          threads=threads, aux_in_gen=ag, split=done % 2, chemT=(done // 2) % 2)
                 assert ret == 0, tag
                 for o_, p_ in zip(out, part):
                     m = ~np.isnan(p_)
