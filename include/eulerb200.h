@@ -185,6 +185,16 @@ int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes);
 /* Number of kernel launches issued through this context so far. */
 int64_t eulerb200_launch_count(const eulerb200_ctx* ctx);
 
+/* Device-time profile of the RHS calls since the last reset, from CUDA events on the streams the
+ * phases run on -- the counterpart of the reference's Profile slots (euler3D.hpp:97-118:
+ * PR_PACKDATA utilities.cpp:87-114, PR_MPI euler3D.hpp:600,789,1179, PR_FACEFLUX, PR_RHSEULER).
+ * on != 0 switches the event recording on (it adds one stream synchronisation per RHS call);
+ * out[8], averages in milliseconds per call: [0] whole call, [1] per-cell pre-pass (aux_kernel),
+ * [2] halo pack kernels, [3] halo transfer (NCCL send/recv or peer stores, on the side stream),
+ * [4] interior kernel, [5] wait for the halo after the interior kernel, [6] boundary shells,
+ * [7] number of calls averaged.  out may be NULL (switch only). */
+int eulerb200_profile(eulerb200_ctx* ctx, int32_t on, int32_t reset, double* out);
+
 /* Measurement aid (no reference counterpart): sustained DFMA throughput of the current
  * device in TFLOP/s, the denominator of the FP64-pipe roofline bench.py reports. */
 int eulerb200_fp64_peak(double* tflops);

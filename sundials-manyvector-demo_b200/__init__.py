@@ -81,6 +81,7 @@ ABI = {
     "eulerb200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),
     "eulerb200_set_forcing_in_wdot": (C.c_int, [C.c_void_p, C.c_int32]),
+    "eulerb200_profile": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "eulerb200_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
 }
 
@@ -335,6 +336,14 @@ class EulerData:
 
     def launch_count(self):
         return int(load_library().eulerb200_launch_count(self._ctx))
+
+    def profile(self, on=True, reset=False):
+        """Device-time profile of the RHS calls since the last reset (eulerb200_profile): dict of
+        average milliseconds per call, the counterpart of the reference's Profile slots."""
+        out = (C.c_double * 8)()
+        self._check(load_library().eulerb200_profile(self._ctx, 1 if on else 0, 1 if reset else 0, out), self._ctx)
+        keys = ("rhs", "prepass", "pack", "transfer", "interior", "halo_wait", "shells", "calls")
+        return dict(zip(keys, [float(x) for x in out]))
 
     def last_error(self):
         return load_library().eulerb200_last_error(self._ctx).decode()

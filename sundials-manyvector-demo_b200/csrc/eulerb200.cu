@@ -159,9 +159,15 @@ struct eulerb200_ctx {
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
   size_t max_smem_set[5][3][3] = {}, carveout_for[5][3][3] = {};   // per kernel instantiation [variant][kind][part]
+  // eulerb200_profile: events T0 start, T1 after the pre-pass, T2 after the pack kernels, T3 after the interior
+  // kernel, T4 after the wait for the halo, T5 end (stream s); C0 / C1 around the transfer (side stream)
+  bool profile_on = false;
+  cudaEvent_t pev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double pacc[7] = {0, 0, 0, 0, 0, 0, 0};
+  double pacc_n = 0;
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
   long ctas_target = 5920;       // EULERB200_CTAS: CTAs a launch aims for when cutting z-segments (tuning)
-  int force_kernel = 0;          // EULERB200_KERNEL=1: allow the AG instantiation for boundary-heavy launches
+  int force_kernel = 1;          // EULERB200_KERNEL=0: never use the AG instantiation for boundary-heavy launches
   int variant = 0;
   int split = 0;                 // EULERB200_SPLIT=1: fluid fields and species in separate launches
   int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
@@ -224,6 +230,9 @@ int fail(eulerb200_ctx* c, int code, const std::string& msg)
     if (r_ != ncclSuccess)                                                                \
       return fail(c, -3, std::string("NCCL error: ") + nccl().GetErrorString(r_) + " in " #call); \
   } while (0)
+
+// eulerb200_profile: record event q on stream st when profiling is on
+#define EB_PREC(c, q, st) do { if ((c)->profile_on) EB_CUDA(c, cudaEventRecord((c)->pev[q], st)); } while (0)
 
 eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* const* wdot)
 {
@@ -354,6 +363,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
     // delaying it (the pack CTAs slip into the SMs as interior CTAs retire)
     EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
     EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+    EB_PREC(c, 6, c->comm_stream);
     for (int f = 0; f < 6; f++) {
       if (!c->remote[f]) continue;
       const long nent = eb::face_len(c->cfg, f) / nv;
@@ -365,6 +375,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
       c->recv_cur[f] = reinterpret_cast<const double*>(c->mailbox + c->slab_off[par][f]);
     }
     EB_CUDA(c, cudaGetLastError());
+    EB_PREC(c, 7, c->comm_stream);
     EB_CUDA(c, cudaEventRecord(c->ev_recv, c->comm_stream));
     c->exchange_open = true;
     return 0;
@@ -379,6 +390,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
   EB_CUDA(c, cudaGetLastError());
   EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
   EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
+  EB_PREC(c, 6, c->comm_stream);
   eb::ExchangeOp ops[12];
   const int nops = eb::exchange_plan(c->cfg, ops);
   EB_NCCL(c, nccl().GroupStart());
@@ -389,6 +401,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
     else EB_NCCL(c, nccl().Recv(c->recv[f], len, ncclDouble, ops[q].peer, c->comm, c->comm_stream));
   }
   EB_NCCL(c, nccl().GroupEnd());
+  EB_PREC(c, 7, c->comm_stream);
   EB_CUDA(c, cudaEventRecord(c->ev_recv, c->comm_stream));
   c->exchange_open = true;
   return 0;
@@ -513,7 +526,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   EB_CREATE(cudaMallocHost(&c->h_alpha, sizeof(double)));
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
-  if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) == 1) ? 1 : 0;
+  if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) != 0) ? 1 : 0;
   if (const char* ev = getenv("EULERB200_CTAS")) c->ctas_target = std::max(1L, atol(ev));
   if (const char* ev = getenv("EULERB200_CHEMT")) c->use_chemT = (atoi(ev) != 0);
   if (c->use_aux)
@@ -572,6 +585,7 @@ int eulerb200_destroy(eulerb200_ctx* c)
     if (c->ev_join[h]) cudaEventDestroy(c->ev_join[h]);
   }
   for (int q = 0; q < 4; q++) if (c->aux[q]) cudaFree(c->aux[q]);
+  for (int q = 0; q < 8; q++) if (c->pev[q]) cudaEventDestroy(c->pev[q]);
   if (c->chemT) cudaFree(c->chemT);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -733,6 +747,26 @@ int eulerb200_rhs_slow(eulerb200_ctx* c, double t, double* const* w, double* con
   return 0;
 }
 
+static int profile_collect(eulerb200_ctx* c)
+{
+  if (!c->profile_on) return 0;
+  EB_CUDA(c, cudaEventSynchronize(c->pev[5]));
+  auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, c->pev[a], c->pev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0; } return (double)ms; };
+  c->pacc[0] += el(0, 5);
+  c->pacc[1] += el(0, 1);
+  if (c->any_remote) {
+    c->pacc[2] += el(1, 2);
+    if (cudaEventSynchronize(c->pev[7]) == cudaSuccess) c->pacc[3] += el(6, 7);
+    c->pacc[4] += el(2, 3);
+    c->pacc[5] += el(3, 4);
+    c->pacc[6] += el(4, 5);
+  } else {
+    c->pacc[4] += el(1, 5);
+  }
+  c->pacc_n += 1.0;
+  return 0;
+}
+
 static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdot, void* stream,
                     int slow_mode, double energy_units)
 {
@@ -749,13 +783,18 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     P.et_rw = const_cast<double*>(w[4]);
   }
   const long n[3] = {P.nx, P.ny, P.nz};
+  EB_PREC(c, 0, s);
   {
     int rc_ = launch_aux(c, P, 0, P.nz, s);
     if (rc_) return rc_;
   }
+  EB_PREC(c, 1, s);
   if (!c->any_remote) {
     const long lo[3] = {0, 0, 0};
-    return launch_box(c, P, lo, n, s);
+    int rc_ = launch_box(c, P, lo, n, s);
+    if (rc_) return rc_;
+    EB_PREC(c, 5, s);
+    return profile_collect(c);
   }
   // Overlap (the structure of utilities.cpp:61 -> 76-116 -> 119 -> 123-195): start the
   // exchange, evaluate every cell whose stencils stay clear of the remote faces, wait for
@@ -770,16 +809,24 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     hi[d] = n[d] - (c->remote[2 * d + 1] ? 3 : 0);
     if (hi[d] <= lo[d]) interior = false;
   }
+  EB_PREC(c, 2, s);
   if (!interior) {
+    EB_PREC(c, 3, s);
     rc = exchange_end(c, s);
     if (rc) return rc;
+    EB_PREC(c, 4, s);
     const long z[3] = {0, 0, 0};
-    return launch_box(c, P, z, n, s);
+    rc = launch_box(c, P, z, n, s);
+    if (rc) return rc;
+    EB_PREC(c, 5, s);
+    return profile_collect(c);
   }
   rc = launch_box(c, P, lo, hi, s);
   if (rc) return rc;
+  EB_PREC(c, 3, s);
   rc = exchange_end(c, s);
   if (rc) return rc;
+  EB_PREC(c, 4, s);
   {
     const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low
     const long b0[3] = {0, 0, hi[2]}, b1[3] = {n[0], n[1], n[2]};                 // z-high
@@ -806,7 +853,8 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
       EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[h], 0));
     }
   }
-  return 0;
+  EB_PREC(c, 5, s);
+  return profile_collect(c);
 }
 
 int eulerb200_state_flag(eulerb200_ctx* c, void* stream, int32_t* bits)
@@ -1018,6 +1066,22 @@ int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes)
 }
 
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
+
+int eulerb200_profile(eulerb200_ctx* c, int32_t on, int32_t reset, double* out)
+{
+  if (!c) return -1;
+  EB_CUDA(c, cudaSetDevice(c->device));
+  if (out) {
+    const double nn = c->pacc_n > 0 ? c->pacc_n : 1.0;
+    for (int q = 0; q < 7; q++) out[q] = c->pacc[q] / nn;
+    out[7] = c->pacc_n;
+  }
+  if (reset) { for (int q = 0; q < 7; q++) c->pacc[q] = 0; c->pacc_n = 0; }
+  if (on && !c->pev[0])
+    for (int q = 0; q < 8; q++) EB_CUDA(c, cudaEventCreate(&c->pev[q]));
+  c->profile_on = on != 0;
+  return 0;
+}
 
 int eulerb200_set_forcing_in_wdot(eulerb200_ctx* c, int32_t on)
 {

@@ -99,33 +99,36 @@ struct StencilPt {
 
 // Resolve the six points pos = idx-3 .. idx+2 along `dir` for the face whose index along
 // that axis is idx (cell coordinates i,j,k hold idx in component dir).
+// Index arithmetic in 32 bits throughout (one IMAD.WIDE then forms base + 8 off per load; in 64 bits
+// every load costs an add-with-carry pair): eulerb200_create refuses boxes of 2^31 cells or more.
 template <bool GEN>
-EB_HD void resolve(const RhsParams& P, int dir, long i, long j, long k, StencilPt pt[6])
+EB_HD void resolve(const RhsParams& P, int dir, int i, int j, int k, StencilPt pt[6])
 {
-  const long stride = (dir == 0) ? 1 : (dir == 1 ? P.nx : P.nx * P.ny);
-  const long idx = (dir == 0) ? i : (dir == 1 ? j : k);
-  const long cell = i + P.nx * (j + P.ny * k);   // may lie one past the end along dir
+  const int nx = (int)P.nx, ny = (int)P.ny;
+  const int stride = (dir == 0) ? 1 : (dir == 1 ? nx : nx * ny);
+  const int idx = (dir == 0) ? i : (dir == 1 ? j : k);
+  const int cell = i + nx * (j + ny * k);   // may lie one past the end along dir
 #pragma unroll
   for (int l = 0; l < 6; l++) {
-    const long pos = idx - 3 + l;
+    const int pos = idx - 3 + l;
     pt[l].off = (unsigned)(cell + (l - 3) * stride);
     pt[l].neg = 0u;
     pt[l].src = -1;
     if (GEN) {
-      const long n = (dir == 0) ? P.nx : (dir == 1 ? P.ny : P.nz);
+      const int n = (dir == 0) ? nx : (dir == 1 ? ny : (int)P.nz);
       if (pos < 0 || pos >= n) {
         const int f = 2 * dir + (pos >= n ? 1 : 0);
         const GhostFace& G = P.ghost[f];
         if (G.mode == GHOST_MAP) {
-          const long mapped = G.a + (long)G.b * pos;
+          const int mapped = (int)G.a + G.b * pos;
           pt[l].off = (unsigned)(cell + (mapped - idx) * stride);
           pt[l].neg = G.neg;
         } else {
-          const long d = (pos < 0) ? pos + 3 : pos - n;
-          const long ta = (dir == 0) ? j : i;
-          const long tb = (dir == 2) ? j : k;
-          const long na = (dir == 0) ? P.ny : P.nx;
-          pt[l].off = (unsigned)((long)(5 + P.nchem) * (d + 3 * (ta + na * tb)));
+          const int d = (pos < 0) ? pos + 3 : pos - n;
+          const int ta = (dir == 0) ? j : i;
+          const int tb = (dir == 2) ? j : k;
+          const int na = (dir == 0) ? ny : nx;
+          pt[l].off = (unsigned)((5 + P.nchem) * (d + 3 * (ta + na * tb)));
           pt[l].src = f;
         }
       }
@@ -193,7 +196,7 @@ EB_HD void point_uc(const RhsParams& P, const StencilPt& pt, int fn, int f1, int
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
 // i.e. of cell (i,j,k) itself (0 from a species-only launch: the fluid launch reports them).
 template <bool GEN, bool AG, int PART, class Emit>
-EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emit)
+EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit)
 {
   StencilPt pt[6];
   resolve<GEN>(P, dir, i, j, k, pt);
@@ -360,7 +363,7 @@ EB_HD int face_all(const RhsParams& P, int dir, long i, long j, long k, Emit emi
 }
 
 template <bool AG, int PART, class Emit>
-EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, long i, long j, long k, Emit emit)
+EB_HD int face_dispatch(bool gen, const RhsParams& P, int dir, int i, int j, int k, Emit emit)
 {
   return gen ? face_all<true, AG, PART>(P, dir, i, j, k, emit) : face_all<false, AG, PART>(P, dir, i, j, k, emit);
 }
@@ -555,29 +558,31 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   long fy_flip = two_fy ? (long)nf * T : 0;         // signed distance to the other FY buffer
   double* ZLO = smem + (long)nf * (TR + (two_fy ? 2L : 1L) * T) + t - (long)v0 * TR;
 
-  const long ti0 = P.lo[0] + (long)blockIdx.x * (TX - 1);
-  const long tj0 = P.lo[1] + (long)blockIdx.y * (TY - 1);
-  const long i = ti0 + tx, j = tj0 + ty;
-  const long k0 = P.lo[2] + (long)blockIdx.z * P.seg_len;
-  const long k1 = (k0 + P.seg_len < P.hi[2]) ? k0 + P.seg_len : P.hi[2];
+  const int nx = (int)P.nx, ny = (int)P.ny, nz = (int)P.nz;
+  const int hix = (int)P.hi[0], hiy = (int)P.hi[1], hiz = (int)P.hi[2];
+  const int ti0 = (int)P.lo[0] + (int)blockIdx.x * (TX - 1);
+  const int tj0 = (int)P.lo[1] + (int)blockIdx.y * (TY - 1);
+  const int i = ti0 + tx, j = tj0 + ty;
+  const int k0 = (int)P.lo[2] + (int)blockIdx.z * P.seg_len;
+  const int k1 = (k0 + P.seg_len < hiz) ? k0 + P.seg_len : hiz;
 
-  const bool row_ok = (ty < TY - 1) && (j < P.hi[1]);
-  const bool col_ok = (tx < TX - 1) && (i < P.hi[0]);
+  const bool row_ok = (ty < TY - 1) && (j < hiy);
+  const bool col_ok = (tx < TX - 1) && (i < hix);
   const bool owns = row_ok && col_ok;                 // this thread owns a cell column
-  const bool need_x = row_ok && (i <= P.hi[0]);       // lower x-face at position i
-  const bool need_y = col_ok && (j <= P.hi[1]);       // lower y-face at position j
+  const bool need_x = row_ok && (i <= hix);           // lower x-face at position i
+  const bool need_y = col_ok && (j <= hiy);           // lower y-face at position j
 
   // CTA-uniform: does any stencil of this tile reach beyond the owned range in x / y?
-  const bool gen_x = (ti0 - 3 < 0) || (ti0 + TX - 1 + 2 >= P.nx);
-  const bool gen_y = (tj0 - 3 < 0) || (tj0 + TY - 1 + 2 >= P.ny);
+  const bool gen_x = (ti0 - 3 < 0) || (ti0 + TX - 1 + 2 >= nx);
+  const bool gen_y = (tj0 - 3 < 0) || (tj0 + TY - 1 + 2 >= ny);
 
   int mask = 0;
 
   // z-face below the first plane of the segment
   if (owns)
-    face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= P.nz, P, 2, i, j, k0, EmitSlot<TRc>{ZLO, TR, nullptr});
+    face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= nz, P, 2, i, j, k0, EmitSlot<TRc>{ZLO, TR, nullptr});
 
-  for (long k = k0; k < k1; k++) {
+  for (int k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (need_x) {
       const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, EmitSlot<TRc>{FX, TR, nullptr});
@@ -596,8 +601,8 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     // ---- phase B: z-face above cell (i,j,k); each flux closes the divergence of its
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
     if (owns) {
-      const long cell = i + P.nx * (j + P.ny * k);
-      face_dispatch<AG, PART>(k + 1 - 3 < 0 || k + 1 + 2 >= P.nz, P, 2, i, j, k + 1,
+      const long cell = i + nx * (j + ny * k);
+      face_dispatch<AG, PART>(k + 1 - 3 < 0 || k + 1 + 2 >= nz, P, 2, i, j, k + 1,
                               EmitDiv<GW, TRc, Tc>{P, FX, FY, ZLO, TR, T, TX, cell, nullptr, nullptr, nullptr, nullptr, false});
     }
     if (EB_ABLATE & 1) {

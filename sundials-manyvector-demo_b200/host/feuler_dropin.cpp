@@ -179,6 +179,22 @@ int fEuler(realtype t, N_Vector w, N_Vector wdot, void* user_data)
     cerr << "\n" << eulerb200_last_error(ctx) << "\n\n";
     return -1;
   }
+  // EULERB200_PROFILE=1: the reference's other profile slots of this path, fed from CUDA events
+  // (device time of this call): PR_PACKDATA = per-cell pre-pass + halo pack kernels (the reference
+  // times pack1D there, utilities.cpp:87-114), PR_MPI = halo transfer + the wait for it
+  // (euler3D.hpp:600,789,1179), PR_FACEFLUX = interior kernel + boundary shells.
+  static const bool profiling = getenv("EULERB200_PROFILE") != NULL && atoi(getenv("EULERB200_PROFILE")) != 0;
+  if (profiling) {
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (eulerb200_profile(ctx, 1, 1, ms) == 0 && ms[7] > 0) {
+      udata->profile[PR_PACKDATA].time += 1e-3 * (ms[1] + ms[2]);
+      udata->profile[PR_PACKDATA].count++;
+      udata->profile[PR_MPI].time += 1e-3 * (ms[3] + ms[5]);
+      udata->profile[PR_MPI].count++;
+      udata->profile[PR_FACEFLUX].time += 1e-3 * (ms[4] + ms[6]);
+      udata->profile[PR_FACEFLUX].count++;
+    }
+  }
 
   retval = udata->profile[PR_RHSEULER].stop();
   if (check_flag(&retval, "Profile::stop (fEuler)", 1)) return -1;
