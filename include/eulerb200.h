@@ -178,6 +178,13 @@ int eulerb200_vec_wrms(eulerb200_ctx* ctx, const double* const* x, const double*
 /* Device-memory helpers so that a C/C++ host driver needs no CUDA headers
  * (N_VNew_* / N_VDestroy and the host<->device copies of a device-vector build). */
 void* eulerb200_device_alloc(int64_t bytes);
+/* Managed memory (cudaMallocManaged): what the reference's own device builds use for the chemistry
+ * sub-vector (N_VNewManaged_Raja, euler3D_main.cpp:158-166) -- host code of an unmodified driver
+ * (initial conditions, diagnostics, I/O) reads and writes it, the RHS and the vector operations run
+ * on it on the device.  Free with eulerb200_device_free. */
+void* eulerb200_managed_alloc(int64_t bytes);
+/* cudaDeviceSynchronize on the context's device: call before host code touches managed vectors. */
+int eulerb200_synchronize(eulerb200_ctx* ctx);
 void eulerb200_device_free(void* p);
 int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes);
 int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes);

@@ -6,6 +6,10 @@
  * ------------------------------------------------------------------------- */
 #include "arkode/arkode_arkstep.h"
 #include "erk_stepper.hpp"
+#ifdef SHIM_MANAGED_VECTORS
+#include "eulerb200.h"
+extern "C" eulerb200_ctx* eulerb200_dropin_context(void* user_data);
+#endif
 
 namespace {
 
@@ -18,6 +22,43 @@ struct NVecOps {
   ARKExpStabFn stab = NULL;
   void* user = NULL;
   void* stab_data = NULL;
+#ifdef SHIM_MANAGED_VECTORS
+  // vectors in managed memory: stage combinations and the error norm run on the device
+  // (eulerb200_vec_lincomb / _wrms_accum), the state never leaves it between outputs
+  eulerb200_ctx* ctx() { return eulerb200_dropin_context(user); }
+  double* d_acc = NULL;
+  void lincomb(Vec& out, int n, const double* c, Vec* const* v)
+  {
+    for (int s = 0; s < out.v->nsub; s++) {
+      const double* x[16];
+      for (int q = 0; q < n; q++) x[q] = v[q]->v->sub[s]->data;
+      if (eulerb200_vec_lincomb(ctx(), n, c, x, out.v->sub[s]->data, out.v->sub[s]->length, NULL) != 0) abort();
+    }
+  }
+  double wrms(const Vec& x, const Vec& y, double rtol, double atol)
+  {
+    if (!d_acc) d_acc = (double*)eulerb200_device_alloc(sizeof(double));
+    double acc[2] = {0.0, 0.0};
+    eulerb200_copy_to_device(d_acc, acc, sizeof(double));
+    for (int s = 0; s < x.v->nsub; s++) {
+      if (eulerb200_vec_wrms_accum(ctx(), x.v->sub[s]->data, y.v->sub[s]->data, rtol, atol, x.v->sub[s]->length, d_acc, NULL) != 0) abort();
+      acc[1] += (double)x.v->sub[s]->length;
+    }
+    eulerb200_copy_to_host(acc, d_acc, sizeof(double));
+    MPI_Allreduce(MPI_IN_PLACE, acc, 2, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+    return std::sqrt(acc[0] / acc[1]);
+  }
+  void copy(N_Vector src, N_Vector dst)
+  {
+    const double one = 1.0;
+    for (int s = 0; s < src->nsub; s++) {
+      const double* x[1] = {src->sub[s]->data};
+      if (eulerb200_vec_lincomb(ctx(), 1, &one, x, dst->sub[s]->data, src->sub[s]->length, NULL) != 0) abort();
+    }
+    eulerb200_synchronize(ctx());      // the driver's host code reads dst next
+  }
+#else
+  void copy(N_Vector src, N_Vector dst) { N_VScale(1.0, src, dst); }
   void lincomb(Vec& out, int n, const double* c, Vec* const* v)
   {
     for (int s = 0; s < out.v->nsub; s++) {
@@ -42,6 +83,7 @@ struct NVecOps {
     MPI_Allreduce(MPI_IN_PLACE, acc, 2, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
     return std::sqrt(acc[0] / acc[1]);
   }
+#endif
   int rhs(double t, Vec& y, Vec& out) { return fe(t, y.v, out.v, user); }
   int stability(Vec& w, double t, double, double* dt) { return stab(w.v, t, dt, stab_data); }
 };
@@ -71,7 +113,7 @@ void* ARKStepCreate(ARKRhsFn fe, ARKRhsFn, realtype t0, N_Vector y0, SUNContext 
   m->S.ops.fe = fe;
   m->S.t = t0;
   m->S.w.v = clone(y0, ctx);
-  N_VScale(1.0, y0, m->S.w.v);
+  N_VScale(1.0, y0, m->S.w.v);          // (host copy: the user data, hence the device context, is not known yet)
   m->S.ytmp.v = clone(y0, ctx);
   m->S.yerr.v = clone(y0, ctx);
   for (int i = 0; i < 13; i++) m->S.k[i].v = clone(y0, ctx);
@@ -113,7 +155,7 @@ int ARKStepEvolve(void* mem, realtype tout, N_Vector yout, realtype* tret, int)
     M->started = true;
   }
   const int rc = M->S.evolve(tout);
-  N_VScale(1.0, M->S.w.v, yout);
+  M->S.ops.copy(M->S.w.v, yout);
   *tret = M->S.t;
   return rc;
 }

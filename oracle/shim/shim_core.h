@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
+#include <stdint.h>
 #include <vector>
 
 /* ------------------------------- SUNDIALS ------------------------------ */
@@ -54,26 +55,45 @@ static inline int SUNMemoryHelper_Destroy(SUNMemoryHelper h) { delete h; return 
 struct shim_NVector_ {
   sunindextype length;
   realtype* data;
-  bool own;
+  int own;             /* 0 borrowed, 1 new[], 2 managed memory (SHIM_MANAGED_VECTORS) */
   int nsub;
   shim_NVector_** sub;
 };
 typedef shim_NVector_* N_Vector;
 
+/* -DSHIM_MANAGED_VECTORS (the refmain_gpu_* programs): the leaf vectors the driver creates with
+ * N_VNew_Serial live in CUDA managed memory, like the N_VNewManaged_* vectors of the reference's own
+ * device builds -- the unmodified driver's host code keeps working on them, the drop-in fEuler and
+ * the vector operations of shim_arkstep.cpp run on the device with the state resident there. */
+#ifdef SHIM_MANAGED_VECTORS
+extern "C" void* eulerb200_managed_alloc(int64_t bytes);
+extern "C" void eulerb200_device_free(void* p);
+#endif
+
 static inline N_Vector N_VNew_Serial(sunindextype n, SUNContext) {
   N_Vector v = new shim_NVector_();
-  v->length = n; v->data = new realtype[n](); v->own = true; v->nsub = 0; v->sub = NULL;
+#ifdef SHIM_MANAGED_VECTORS
+  v->length = n; v->data = (realtype*)eulerb200_managed_alloc((int64_t)sizeof(realtype) * n); v->own = 2;
+  if (!v->data) { fprintf(stderr, "shim: eulerb200_managed_alloc failed\n"); abort(); }
+  memset(v->data, 0, sizeof(realtype) * n);
+  v->nsub = 0; v->sub = NULL;
+#else
+  v->length = n; v->data = new realtype[n](); v->own = 1; v->nsub = 0; v->sub = NULL;
+#endif
   return v;
 }
 static inline N_Vector N_VMake_Serial(sunindextype n, realtype* data, SUNContext) {
   N_Vector v = new shim_NVector_();
-  v->length = n; v->data = data; v->own = false; v->nsub = 0; v->sub = NULL;
+  v->length = n; v->data = data; v->own = 0; v->nsub = 0; v->sub = NULL;
   return v;
 }
 static inline realtype* N_VGetArrayPointer(N_Vector v) { return v ? v->data : NULL; }
 static inline void N_VDestroy(N_Vector v) {
   if (!v) return;
-  if (v->own && v->data) delete[] v->data;
+#ifdef SHIM_MANAGED_VECTORS
+  if (v->own == 2 && v->data) eulerb200_device_free(v->data);
+#endif
+  if (v->own == 1 && v->data) delete[] v->data;
   if (v->sub) delete[] v->sub;
   delete v;
 }
@@ -138,7 +158,7 @@ static inline int MPI_Reduce(const void* in, void* out, int count, MPI_Datatype 
 
 static inline N_Vector N_VMake_MPIManyVector(MPI_Comm, sunindextype nsub, N_Vector* subs, SUNContext) {
   N_Vector v = new shim_NVector_();
-  v->length = 0; v->data = NULL; v->own = false; v->nsub = (int)nsub;
+  v->length = 0; v->data = NULL; v->own = 0; v->nsub = (int)nsub;
   v->sub = new shim_NVector_*[nsub];
   for (int s = 0; s < (int)nsub; s++) { v->sub[s] = subs[s]; v->length += subs[s]->length; }
   return v;

@@ -77,6 +77,8 @@ ABI = {
                                     C.POINTER(C.c_double), C.c_void_p]),
     "eulerb200_device_alloc": (C.c_void_p, [C.c_int64]),
     "eulerb200_device_free": (None, [C.c_void_p]),
+    "eulerb200_managed_alloc": (C.c_void_p, [C.c_int64]),
+    "eulerb200_synchronize": (C.c_int, [C.c_void_p]),
     "eulerb200_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "eulerb200_launch_count": (C.c_int64, [C.c_void_p]),

@@ -8,7 +8,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeulerb200.so")
 SOURCES = ["eulerb200.cu"]
-HEADERS = ["rhs_kernel.cuh", "halo_kernels.cuh", "vector_kernels.cuh", "euler_math.cuh", "host_setup.h", os.path.join("..", "..", "include", "eulerb200.h")]
+HEADERS = ["rhs_kernel.cuh", "strict_face.cuh", "halo_kernels.cuh", "vector_kernels.cuh", "euler_math.cuh", "host_setup.h", os.path.join("..", "..", "include", "eulerb200.h")]
+# the STRICT build (csrc/strict_face.cuh): reference operation order, no FMA contraction, IEEE division --
+# bit-identical to the reference; a verification artefact (tests/test_gpu_strict.py), never the default
+LIB_STRICT = os.path.join(HERE, "libeulerb200_strict.so")
+STRICT_FLAGS = ["-DEB_STRICT", "-DEB_FAST_BUILD", "-fmad=false"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -24,25 +28,29 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=None):
+    lib = lib or LIB
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libeulerb200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    jobs = []
+    for lib, extra in ((LIB, []), (LIB_STRICT, STRICT_FLAGS)):
+        if force or needs_build(lib):
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+                  ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+            jobs.append((lib, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for lib, proc in jobs:          # the two builds run side by side
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed building %s" % os.path.basename(lib))
+        if verbose:
+            sys.stderr.write(out)
     return LIB
 
 

@@ -242,6 +242,7 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   P.nchem = g.nchem;
   P.gamma = g.gamma;
   P.rdx = 1.0 / g.dx; P.rdy = 1.0 / g.dy; P.rdz = 1.0 / g.dz;
+  P.dx = g.dx; P.dy = g.dy; P.dz = g.dz;
   for (int f = 0; f < 5; f++) P.forcing[f] = g.forcing[f];
   for (int f = 0; f < 6; f++) {
     P.w[f] = (f < 5 || g.nchem > 0) ? w[f] : nullptr;
@@ -312,6 +313,10 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
   else if (c->force_kernel == 1 && c->use_aux) {
     const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, 5 + P.nchem, kVariants[c->variant_part[0]].threads, c->pair_sync, c->ctas_target);
     if (eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) kind = 1;
+  }
+  if (!kVariants[kGenericVariant].fn[kind][0]) {      // reduced builds (tuning, strict) compile the default kind only
+    if (kind == 2) return fail(c, -1, "this build of the library has no hook-assigned-forcing instantiation");
+    kind = 0;
   }
   int rc;
   if (c->split && P.nchem > 0) {
@@ -1056,6 +1061,19 @@ void* eulerb200_device_alloc(int64_t bytes)
   return p;
 }
 void eulerb200_device_free(void* p) { if (p) cudaFree(p); }
+void* eulerb200_managed_alloc(int64_t bytes)
+{
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocManaged(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+int eulerb200_synchronize(eulerb200_ctx* c)
+{
+  if (!c) return -1;
+  EB_CUDA(c, cudaSetDevice(c->device));
+  EB_CUDA(c, cudaDeviceSynchronize());
+  return 0;
+}
 int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes)
 {
   return cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : fail(nullptr, -2, "cudaMemcpy H2D failed");

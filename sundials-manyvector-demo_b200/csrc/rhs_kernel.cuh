@@ -28,6 +28,9 @@
 // ---------------------------------------------------------------------------
 #pragma once
 #include "euler_math.cuh"
+#ifdef EB_STRICT
+#include "strict_face.cuh"
+#endif
 
 // EB_ABLATE: bit mask of measurement-only ablations used by tools/ablate.cu to attribute kernel time
 // (1 no barriers, 2 species values synthesised instead of loaded, 4 results not stored, 8 the
@@ -62,6 +65,7 @@ struct RhsParams {
   int seg_len;              // cells per z-segment
   double gamma;
   double rdx, rdy, rdz;     // 1/dx, 1/dy, 1/dz
+  double dx, dy, dz;        // (the strict build divides as the reference does, utilities.cpp:202-207)
   double forcing[5];        // constant forcing assigned into wdot (external_forces hook)
   const double* w[6];       // rho, mx, my, mz, et (SoA), chem (AoS, species fastest)
   double* wdot[6];
@@ -206,6 +210,33 @@ EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit)
   const int f1 = (dir == 1) ? 1 : 2;
   const int f2 = (dir == 2) ? 1 : 3;
 
+#ifdef EB_STRICT
+  {
+    // the reference's arithmetic, operation for operation (strict_face.cuh): gather the stencil as
+    // pack1D_* does (euler3D.hpp:1197-1378), face_flux, hand the fluxes on
+    const int nvar = 5 + P.nchem;
+    double s[6][strict::MAXVAR], f[strict::MAXVAR];
+    for (int l = 0; l < 6; l++) {
+      for (int v = 0; v < 5; v++) s[l][v] = load_fluid<GEN>(P, pt[l], v);
+      for (int v = 0; v < P.nchem; v++) {
+        const double x = (GEN && pt[l].src >= 0) ? P.ghost[pt[l].src].buf[pt[l].off + 5 + v]
+                                                 : P.w[5][(long)pt[l].off * P.nchem + v];
+        s[l][5 + v] = (GEN && ((pt[l].neg >> 5) & 1u)) ? -x : x;
+      }
+    }
+    const double p3 = strict::eos(P.gamma, s[3][0], s[3][1], s[3][2], s[3][3], s[3][4]);
+    const int sbits = ((s[3][0] > 0.0) ? 0 : 1) | ((s[3][4] > 0.0) ? 0 : 2) | ((p3 > 0.0) ? 0 : 4);
+    strict::face_flux(s, nvar, dir, P.gamma, f);
+    if (PART != PART_TRACERS)
+      for (int v = 0; v < 5; v++) emit(v, f[v]);
+    if (PART != PART_FLUID && P.nchem > 0) {
+      emit.species_begin();
+      for (int v = 0; v < P.nchem; v += 2) emit.pair_next(f[5 + v], (v + 1 < P.nchem) ? f[6 + v] : 0.0, v + 1 < P.nchem);
+    }
+    (void)fn; (void)f1; (void)f2;
+    return (PART != PART_TRACERS) ? sbits : 0;
+  }
+#else
   double alpha, u[6];
   int bits = 0;
   if (PART != PART_TRACERS) {
@@ -360,6 +391,7 @@ EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit)
     }
   }
   return bits;
+#endif  // EB_STRICT
 }
 
 template <bool AG, int PART, class Emit>
@@ -400,8 +432,13 @@ struct EmitDiv {
   EB_HD int T() const { return Tc > 0 ? Tc : rT; }
   EB_HD double close(int v, double zup) const
   {
+#if defined(EB_STRICT) || defined(EB_TRUE_DIVISION)
+    const double div = ((FX[v * TR() + 1] - FX[v * TR()]) / P.dx + (FY[v * T() + TX] - FY[v * T()]) / P.dy)
+                       + (zup - ZLO[v * TR()]) / P.dz;
+#else
     const double div = ((FX[v * TR() + 1] - FX[v * TR()]) * P.rdx + (FY[v * T() + TX] - FY[v * T()]) * P.rdy)
                        + (zup - ZLO[v * TR()]) * P.rdz;
+#endif
     ZLO[v * TR()] = zup;
     return div;
   }
@@ -420,8 +457,13 @@ struct EmitDiv {
   }
   EB_HD double close_next(int q, double zup) const      // q-th species (0 / 1) at the running pointers
   {
+#if defined(EB_STRICT) || defined(EB_TRUE_DIVISION)
+    return ((fx[q * TR() + 1] - fx[q * TR()]) / P.dx + (fy[q * T() + TX] - fy[q * T()]) / P.dy)
+           + (zup - zl[q * TR()]) / P.dz;
+#else
     return ((fx[q * TR() + 1] - fx[q * TR()]) * P.rdx + (fy[q * T() + TX] - fy[q * T()]) * P.rdy)
            + (zup - zl[q * TR()]) * P.rdz;
+#endif
   }
   EB_HD void pair_next(double za, double zb, bool two)    // two == false: the odd species out, zb unused
   {
@@ -510,10 +552,14 @@ __global__ void slow_post_kernel(const RhsParams P)
 }
 
 #if defined(__CUDACC__)
-// named barrier: `count` threads (whole warps) meet at hardware barrier `id` (1..15)
+// named barrier: `count` threads (whole warps) meet at hardware barrier `id` (1..15).  The count is
+// always 64 here (two neighbouring warp rows) and is given as an immediate: with a register operand
+// compute-sanitizer's synccheck cannot see that the barrier is a partial one and reports the other
+// rows as divergent.
 __device__ __forceinline__ void eb_bar_sync(int id, int count)
 {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  (void)count;
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 #endif
 

@@ -280,7 +280,10 @@ class ERKStep:
                     eta = 1.0
                 self.ehist = [max(dsm, 1e-10), self.ehist[0]]
                 self.h = max(h * eta, self.o.hmin)
-        self.t = tout
+        # snap onto tout only across round-off: a tout at or behind the clock leaves it alone
+        # (ARKStepEvolve in ARK_NORMAL mode never rewinds the integrator)
+        if abs(self.t - tout) <= 1e-14 * max(abs(tout), 1.0) + 1e-300:
+            self.t = tout
         return 0, self.t
 
     def set_fixed_step(self, h):

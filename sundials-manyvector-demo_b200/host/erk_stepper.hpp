@@ -110,7 +110,9 @@ struct ErkStepper {
         h = std::max(hh * eta, hmin);
       }
     }
-    t = tout;
+    // snap onto tout only across round-off: a tout at or behind the clock leaves it alone
+    // (ARKStepEvolve in ARK_NORMAL mode never rewinds the integrator)
+    if (fabs(t - tout) <= 1e-14 * std::max(fabs(tout), 1.0) + 1e-300) t = tout;
     return failed ? -1 : 0;
   }
 };

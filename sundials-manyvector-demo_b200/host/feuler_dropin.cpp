@@ -148,6 +148,13 @@ int subvector_pointers(N_Vector v, int nchem, const char* who, double* out[6])
 
 }  // namespace
 
+// The device context bound to an EulerData (created on first use): for callers that run their vector
+// operations on the device next to the RHS (a CUDA / managed N_Vector build of the driver).
+extern "C" eulerb200_ctx* eulerb200_dropin_context(void* user_data)
+{
+  return context_for((EulerData*)user_data);
+}
+
 // Release the device context bound to an EulerData (call next to EulerData::FreeData).
 extern "C" void eulerb200_dropin_release(void* user_data)
 {

@@ -13,13 +13,20 @@ SO = os.path.join(HERE, "libemu.so")
 _dp = C.POINTER(C.c_double)
 
 
-def build():
+def build(strict=False, flags=None, tag=None):
+    """strict: the kernel source with -DEB_STRICT (csrc/strict_face.cuh: the reference's operation order).
+    flags / tag: extra compiler flags and the library-name suffix of a variant build (tools/blast_tolerance.py)."""
+    so = SO.replace("libemu.so", "libemu_strict.so") if strict else SO
+    if tag:
+        so = SO.replace("libemu.so", "libemu_%s.so" % tag)
     deps = [os.path.join(HERE, f) for f in ("emu_rhs.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "halo_kernels.cuh", "vector_kernels.cuh", "euler_math.cuh", "host_setup.h")]
-    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared", "-ffp-contract=off",
-                               "-o", SO, os.path.join(HERE, "emu_rhs.cpp")])
-    return SO
+           [os.path.join(CSRC, f) for f in ("rhs_kernel.cuh", "strict_face.cuh", "halo_kernels.cuh", "vector_kernels.cuh",
+                                            "euler_math.cuh", "host_setup.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fPIC", "-shared"] +
+                              (flags if flags is not None else ["-ffp-contract=off"]) +
+                              (["-DEB_STRICT"] if strict else []) + ["-o", so, os.path.join(HERE, "emu_rhs.cpp")])
+    return so
 
 
 def _ptrs(arrs):
@@ -31,9 +38,9 @@ def _ptrs(arrs):
 
 
 class Emu:
-    def __init__(self, pkg):
+    def __init__(self, pkg, strict=False, flags=None, tag=None):
         self.pkg = pkg
-        self.lib = C.CDLL(build())
+        self.lib = C.CDLL(build(strict, flags, tag))
         self.lib.emu_rhs.restype = C.c_int
 
     def _config(self, n, nchem, d, gamma, bcs, nbr, rank):

@@ -67,6 +67,8 @@ void eulerb200_device_free(void* p) { free(p); }
 int eulerb200_copy_to_device(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
 int eulerb200_copy_to_host(void* dst, const void* src, int64_t bytes) { memcpy(dst, src, (size_t)bytes); return 0; }
 int64_t eulerb200_launch_count(const eulerb200_ctx* c) { return c ? c->launches : -1; }
+void* eulerb200_managed_alloc(int64_t bytes) { return bytes > 0 ? malloc((size_t)bytes) : nullptr; }
+int eulerb200_synchronize(eulerb200_ctx* c) { return c ? 0 : -1; }
 int eulerb200_profile(eulerb200_ctx* c, int32_t, int32_t, double* out) { if (!c) return -1; if (out) for (int q = 0; q < 8; q++) out[q] = 0.0; return 0; }
 // the product's lincomb_kernel / wrms_kernel (vector_kernels.cuh) through the emulator
 int eulerb200_vec_lincomb(eulerb200_ctx* c, int32_t nterms, const double* coef, const double* const* x, double* out,

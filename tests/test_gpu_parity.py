@@ -108,12 +108,17 @@ def test_blast_states_match_oracle(pkg, port, port_fma, problem, nchem):
     got = [s.cpu().numpy() for s in wdot.sub] + ([None] if nchem == 0 else [])
     # c^2 ~ 1e-7 ... 1e-9 in code units here: the eigenvector matrices carry 1/c^2 (utilities.cpp:
     # 309-364) and the reference itself moves by up to 5e-11 when recompiled with FMA contraction.
-    # Bar: 1e-12, or 8x that self-noise where it is larger.
+    # Bar: 1e-12, or 1.5x that self-noise where it is larger, with NO rounding floor subtracted.
+    # Measured on B200: 1.06x (rho, fluid_blast), 0.76x (e_t), <= 0.8x (primordial_blast) -- two
+    # independent roundings of the same quantity, so their maxima over the grid differ by a factor of
+    # order one either way; profiles/r2_blast_tolerance.md shows every re-association of the kernel's
+    # arithmetic at or below the reference's own FMA self-noise on these states, and the strict build
+    # (tests/test_gpu_strict.py) is bit-identical.
     cfg = port.cfg(n, nchem, (u.dx, u.dy, u.dz), u.gamma, u.bcs, forcing=u.forcing)
     noise = self_noise(port, port_fma, cfg, parts)
-    errs = normwise_errors(got, ref, rounding_floor(parts, u.gamma, (u.dx, u.dy, u.dz)))
+    errs = normwise_errors(got, ref)
     for e, nz in zip(errs, noise):
-        assert e <= max(TOL, 8.0 * nz), (errs, noise)
+        assert e <= max(TOL, 1.5 * nz), (errs, noise)
     if nchem:                       # per species too: each tracer against its own scale
         g5, r5 = got[5].reshape(-1, nchem), ref[5].reshape(-1, nchem)
         c5 = parts[5].reshape(-1, nchem)

@@ -166,6 +166,29 @@ def test_emulated_split_launches_equal_the_fused_launch(emu, oracle_mod, port, n
     assert r0[0] == r1[0] == -1 and r0[2] == r1[2] != 0
 
 
+def test_emulated_strict_build_is_bit_identical_to_the_oracle(pkg, oracle_mod, port):
+    """-DEB_STRICT (csrc/strict_face.cuh): the reference's face_flux arithmetic operation for operation
+    and true divisions in the divergence.  Compiled without FMA contraction the kernel source then
+    reproduces the oracle BIT FOR BIT -- stencil resolution, every ghost rule, tile and z-segment seams,
+    the shared-memory flux exchange, split launches, sub-boxes -- so whatever the fast build differs by
+    is rounding of its re-derived arithmetic and nothing else."""
+    from emu.emu import Emu
+    emu_s = Emu(pkg, strict=True)
+    cases = [((12, 9, 7), 0, [P] * 6, 256, {}), ((12, 9, 7), 2, [N] * 6, 384, {}), ((12, 9, 7), 3, [R] * 6, 256, {}),
+             ((35, 10, 5), 2, [P, P, R, R, N, N], 128, dict(pair=1)), ((3, 20, 17), 2, [N] * 6, 256, {}),
+             ((40, 3, 3), 0, [N] * 6, 256, {}), ((7, 6, 26), 4, [R, R, P, P, N, N], 64, dict(split=1)),
+             ((70, 12, 10), 10, [R] * 6, 384, dict(pair=2)), ((33, 9, 4), 24, [N] * 6, 384, {})]
+    for n, nchem, bcs, threads, kw in cases:
+        w = oracle_mod.random_state(n, nchem, seed=sum(n))
+        d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+        forcing = [0, 0.25, -0.1, 0, 0.5]
+        ret, got, bits = emu_s.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, **kw)
+        ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs, forcing=forcing), w)
+        assert ret == 0 and ret_ref == 0 and bits == 0
+        for a, b in zip(got, ref):
+            assert (a is None and b is None) or np.array_equal(a, b), (n, nchem, bcs)
+
+
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)
