@@ -499,7 +499,10 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     return fail(nullptr, -2, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
   eulerb200_ctx* c = new eulerb200_ctx();
   c->cfg = *cfg;
-  c->variant = kDefaultVariant;
+  // 384 threads (168 registers) with species; without them the flux arrays are small, the 128-register
+  // build spills little and 16 warps per SM win (measured at 512^3: 27.6 vs 29.3 ms; with ten species
+  // 65.4 vs 61.7 ms the other way round, profiles/README.md)
+  c->variant = (cfg->nchem == 0) ? 2 : kDefaultVariant;
   if (const char* ev = getenv("EULERB200_VARIANT")) {
     const int v = atoi(ev);
     if (v >= 0 && v < kNumVariants) c->variant = v;
