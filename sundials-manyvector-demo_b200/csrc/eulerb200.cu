@@ -158,7 +158,7 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set[5][3][3] = {}, carveout_for[5][3][3] = {};   // per kernel instantiation [variant][kind][part]
+  size_t max_smem_set[6][3][3] = {}, carveout_for[6][3][3] = {};   // per kernel instantiation [variant][kind][part]
   // eulerb200_profile: events T0 start, T1 after the pre-pass, T2 after the pack kernels, T3 after the interior
   // kernel, T4 after the wait for the halo, T5 end (stream s); C0 / C1 around the transfer (side stream)
   bool profile_on = false;
@@ -170,6 +170,7 @@ struct eulerb200_ctx {
   int force_kernel = 1;          // EULERB200_KERNEL=0: never use the AG instantiation for boundary-heavy launches
   int variant = 0;
   int split = 0;                 // EULERB200_SPLIT=1: fluid fields and species in separate launches
+  int stage = 0;                 // EULERB200_STAGE=1: the bulk-copy staging variant of the fused kernel (A/B)
   int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
@@ -208,8 +209,12 @@ const KernelVariant kVariants[] = {
     {EB_KERNELS_FULL(512, 1, 16), 512, "512x1 (<=128 regs)"},
     {EB_KERNELS_PLAIN(640, 1, 20), 640, "640x1 (<=96 regs)"},
     {EB_KERNELS_FULL(384, 1, 0), 384, "any tile shape, <= 384 threads"},
+    // A/B variant (EULERB200_STAGE=1): species of the current plane staged in shared memory by cp.async.bulk
+    {{{eb::rhs_fused_kernel<384, 1, false, false, eb::PART_ALL, 12, true>, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}},
+     384, "384x1, bulk-copy staging of the species plane"},
 };
 const int kGenericVariant = 4;
+const int kStageVariant = 5;
 const int kNumVariants = 4;    // selectable; the last entry is the any-shape fallback
 const int kDefaultVariant = 1;
 
@@ -275,6 +280,16 @@ int launch_part(eulerb200_ctx* c, eb::RhsParams P, int kind, int part, cudaStrea
     // default variant only: the any-shape instantiation
     vi = kGenericVariant;
     L = eb::launch_geom(P.lo, P.hi, nf, kVariants[vi].threads, c->pair_sync, c->ctas_target);
+  }
+  if (c->stage && kind == 0 && part == eb::PART_ALL && vi == kDefaultVariant && P.vec_store && !P.chemT) {
+    // the staging variant: CTA-wide barriers, and room for the (TX+5) x (TY+5) x nchem window + the mbarrier
+    const size_t extra = sizeof(double) * (size_t)(L.tx + 5) * (L.ty + 5) * P.nchem + 16;
+    eb::LaunchGeom Ls = eb::launch_geom(P.lo, P.hi, nf, kVariants[kStageVariant].threads, 0, c->ctas_target);
+    if (Ls.tx == L.tx && Ls.ty == L.ty && Ls.smem + extra <= (size_t)227 * 1024) {
+      vi = kStageVariant;
+      L = Ls;
+      L.smem += extra;
+    }
   }
   const KernelVariant& V = kVariants[vi];
   void (*const fn)(const eb::RhsParams) = V.fn[kind][part];
@@ -512,7 +527,8 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_VARIANT_F")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[1] = v; }
   if (const char* ev = getenv("EULERB200_VARIANT_T")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[2] = v; }
   if (const char* ev = getenv("EULERB200_SPLIT")) c->split = atoi(ev) != 0;
-  for (int a_ = 0; a_ < 5; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
+  if (const char* ev = getenv("EULERB200_STAGE")) c->stage = atoi(ev) != 0;
+  for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
   if (cfg->device >= 0) {
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }

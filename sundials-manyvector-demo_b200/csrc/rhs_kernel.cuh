@@ -199,8 +199,10 @@ EB_HD void point_uc(const RhsParams& P, const StencilPt& pt, int fn, int f1, int
 // handed to emit(v, value) with v in the reference's field order (rho,mx,my,mz,et,
 // tracers...).  Returns the legal_state bits (euler3D.hpp:1405-1414) of stencil point 3,
 // i.e. of cell (i,j,k) itself (0 from a species-only launch: the fluid launch reports them).
-template <bool GEN, bool AG, int PART, class Emit>
-EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit)
+// STG: the species values of the six stencil points come from the shared-memory copy of the plane
+// (rhs_fused_kernel<..., STAGE>): pair q of point l at sb[l * ss + q].
+template <bool GEN, bool AG, int PART, class Emit, bool STG = false>
+EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit, const double2* sb = nullptr, int ss = 0)
 {
   StencilPt pt[6];
   resolve<GEN>(P, dir, i, j, k, pt);
@@ -337,12 +339,12 @@ EB_HD int face_all(const RhsParams& P, int dir, int i, int j, int k, Emit emit)
       const int npf = P.nchem / 2;              // full pairs; an odd species count leaves one behind
       // pair q of stencil point l is at qb[io[l]]: one 64-bit base for all six points, advanced once
       // per pair, and 32-bit offsets (one IMAD.WIDE per load)
-      const double2* qb = reinterpret_cast<const double2*>(vec_aos ? P.w[5] : P.chemT);
+      const double2* qb = STG ? sb : reinterpret_cast<const double2*>(vec_aos ? P.w[5] : P.chemT);
       const unsigned istride = vec_aos ? (unsigned)npf : 1u;
-      const long qstep = vec_aos ? 1 : N;
+      const long qstep = (STG || vec_aos) ? 1 : N;
       unsigned io[6];
 #pragma unroll
-      for (int l = 0; l < 6; l++) io[l] = pt[l].off * istride;
+      for (int l = 0; l < 6; l++) io[l] = STG ? (unsigned)(l * ss) : pt[l].off * istride;
       // Slots 0 .. npf-1 hold two species, slot npf (odd nchem, chemT only) one.  The next slot is
       // loaded while the current one is reconstructed; the loop body is branch-free on purpose (the
       // last iteration re-loads its own slot: a conditional load here makes ptxas spill ~4 KB).
@@ -561,6 +563,36 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
   (void)count;
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
+
+// ---- bulk-copy staging (rhs_fused_kernel<..., STAGE>): one elected thread issues cp.async.bulk copies
+// global -> shared (SASS: UBLKCP) that complete on an mbarrier; every thread waits on its phase.
+__device__ __forceinline__ unsigned eb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void eb_mbar_init(unsigned long long* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(eb_smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void eb_mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(eb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void eb_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(eb_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(eb_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void eb_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "EB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra EB_DONE;\n"
+      "bra EB_WAIT;\n"
+      "EB_DONE:\n"
+      "}\n" ::"r"(eb_smem_addr(bar)), "r"(parity) : "memory");
+}
 #endif
 
 // Dynamic shared memory: FX [NF][T-TX], FY [NF][T] (exchanged with the +x / +y neighbour
@@ -585,7 +617,14 @@ __device__ __forceinline__ void eb_bar_sync(int id, int count)
 // PART: all fields, or the fluid fields / the species only (two launches, see the enum).
 // TYC: 0, or the number of tile rows of a launch whose CTAs are 32 x TYC threads (tile shape and
 // shared-memory strides are then compile-time constants).
-template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL, int TYC = 0>
+// STAGE (A/B variant, EULERB200_STAGE=1; needs TYC > 0, an even species count and CTA-wide barriers): tiles
+// whose x- and y-stencils stay inside the box keep the species of the CURRENT plane -- tile plus
+// three halo cells, (TX+5) x (TY+5) cells x nchem values, rows of the species-fastest vector are
+// contiguous -- in shared memory, filled by cp.async.bulk copies that one thread issues for plane k+1
+// while the z-faces of plane k are computed; the x- and y-face species loops then read shared memory
+// (16-byte loads at stride 8 nchem B: conflict-free per quarter warp for nchem = 10) instead of 19
+// cache lines per load.  The z-stencil (six planes) cannot be staged: 6 x tile x 8 nchem B = 184 KB.
+template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL, int TYC = 0, bool STAGE = false>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
   EB_DYN_SMEM(double, smem);
@@ -595,8 +634,8 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   // fields of this launch: v0 .. v0+nf-1 in the reference's order
   const int v0 = (PART == PART_TRACERS) ? 5 : 0;
   const int nf = (PART == PART_ALL) ? 5 + P.nchem : (PART == PART_FLUID ? 5 : P.nchem);
-  const bool pair = P.pair_sync != 0;
-  const bool two_fy = P.pair_sync == 1;
+  const bool pair = !STAGE && P.pair_sync != 0;          // (STAGE re-fills the staged plane behind a CTA-wide barrier)
+  const bool two_fy = !STAGE && P.pair_sync == 1;
   // the face-only top row of the tile never touches FX / ZLO: those arrays are [NF][TR]
   const int TR = T - TX;
   double* FX = smem + t - (long)v0 * TR;               // indexed with the global field number v
@@ -624,18 +663,58 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
   int mask = 0;
 
+  // ---- STAGE: shared-memory copy of the species of the current plane
+  const int SW = TX + 5;                                   // cells per staged row
+  double2* stage = nullptr;
+  unsigned long long* mbar = nullptr;
+  bool staged = false;
+  unsigned sphase = 0;
+  if (STAGE) {
+    double* after = smem + (long)nf * (2L * TR + T);        // (single FY buffer: STAGE runs with CTA-wide barriers)
+    stage = reinterpret_cast<double2*>(after);
+    mbar = reinterpret_cast<unsigned long long*>(after + (long)SW * (TY + 5) * P.nchem);
+    staged = !gen_x && !gen_y && P.nchem > 0;              // CTA-uniform
+    if (staged) {
+      if (t == 0) eb_mbar_init(mbar, 1);
+      __syncthreads();
+    }
+  }
+  auto stage_plane = [&](int k) {                          // thread 0: species rows tj0-3 .. tj0+TY+1 of plane k
+    const unsigned row_bytes = (unsigned)(SW * P.nchem * sizeof(double));
+    eb_mbar_expect_tx(mbar, row_bytes * (unsigned)(TY + 5));
+    for (int r = 0; r < TY + 5; r++)
+      eb_bulk_g2s(reinterpret_cast<double*>(stage) + (long)r * SW * P.nchem,
+                  P.w[5] + ((long)(ti0 - 3) + (long)nx * ((tj0 - 3 + r) + (long)ny * k)) * P.nchem, row_bytes, mbar);
+  };
+  if (STAGE && staged && t == 0) stage_plane(k0);
+  const int npf = P.nchem / 2;
+
   // z-face below the first plane of the segment
   if (owns)
     face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= nz, P, 2, i, j, k0, EmitSlot<TRc>{ZLO, TR, nullptr});
 
   for (int k = k0; k < k1; k++) {
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
+    if (STAGE && staged) {
+      eb_mbar_wait(mbar, sphase);                          // plane k has landed
+      sphase ^= 1u;
+      // species of cell (row r, column c) of the staged window: stage[(r SW + c) npf + q]
+      if (need_x) {
+        const int bits = face_all<false, AG, PART, EmitSlot<TRc>, true>(P, 0, i, j, k, EmitSlot<TRc>{FX, TR, nullptr},
+                                                                       stage + ((ty + 3) * SW + tx) * npf, npf);
+        if (owns) mask |= bits;
+      }
+      if (need_y)
+        face_all<false, AG, PART, EmitSlot<Tc>, true>(P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr},
+                                                      stage + (ty * SW + tx + 3) * npf, SW * npf);
+    } else {
     if (need_x) {
       const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, EmitSlot<TRc>{FX, TR, nullptr});
       if (owns) mask |= bits;
     }
     if (need_y)
       face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr});
+    }
     if (EB_ABLATE & 1) {
     } else if (pair) {
       if (ty > 0) eb_bar_sync(ty, 64);
@@ -643,6 +722,10 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     } else {
       __syncthreads();
     }
+
+    // every thread is past its reads of the staged plane (CTA-wide barrier above): fetch the next one
+    // behind the z-faces
+    if (STAGE && staged && t == 0 && k + 1 < k1) stage_plane(k + 1);
 
     // ---- phase B: z-face above cell (i,j,k); each flux closes the divergence of its
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----

@@ -156,6 +156,27 @@ inline void __syncwarp()
   const int T = emu_block_threads(), w = cuda_emu::current() / 32;
   cuda_emu::barrier_wait(16 + w, (T - 32 * w < 32) ? T - 32 * w : 32);
 }
+// cp.async.bulk + mbarrier (rhs_fused_kernel<..., STAGE>): the copy happens at issue; the barrier's
+// phase flips when the expected bytes have arrived; a waiting fibre yields until then.
+struct EmuMbar { unsigned phase; long pending; };
+inline EmuMbar* emu_mbar(unsigned long long* bar) { return reinterpret_cast<EmuMbar*>(bar); }
+inline void eb_mbar_init(unsigned long long* bar, int) { emu_mbar(bar)->phase = 0; emu_mbar(bar)->pending = 0; }
+inline void eb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu_mbar(bar)->pending += bytes; }
+inline void eb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  memcpy(dst, src, bytes);
+  EmuMbar* m = emu_mbar(bar);
+  m->pending -= bytes;
+  if (m->pending == 0) m->phase ^= 1u;
+}
+inline void eb_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  long spins = 0;
+  while (emu_mbar(bar)->phase == parity) {
+    if (++spins > 100000000L) { fprintf(stderr, "cuda_emu: mbarrier never completes\n"); abort(); }
+    cuda_emu::yield_to_scheduler();
+  }
+}
 inline int atomicOr(int* addr, int v) { int old = *addr; *addr = old | v; return old; }
 inline double atomicAdd(double* addr, double v) { const double old = *addr; *addr = old + v; return old; }
 inline unsigned long long atomicMax(unsigned long long* addr, unsigned long long v)

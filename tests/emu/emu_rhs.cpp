@@ -10,7 +10,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT)
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT, int stage)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -74,6 +74,14 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
       else if (L.tx == 32 && L.ty == 4) EMU_PARTS(GW, AG, 4);                                                         \
       else EMU_PARTS(GW, AG, 0);                                                                                      \
     } while (0)
+    // the bulk-copy staging variant (launch_part(): default kind, fused launch, 32 x 12 tile, CTA-wide barriers)
+    if (stage && !g_in_wdot && !aux_in_gen && part == eb::PART_ALL && L.tx == 32 && L.ty == 12 && P.vec_store && !P.chemT) {
+      L = eb::launch_geom(P.lo, P.hi, nf, threads, 0);
+      P.pair_sync = 0;
+      L.smem += sizeof(double) * (size_t)(L.tx + 5) * (L.ty + 5) * P.nchem + 16;
+      cuda_emu::launch(eb::rhs_fused_kernel<256, 1, false, false, eb::PART_ALL, 12, true>, dim3(L.gx, L.gy, L.gz), dim3(L.tx, L.ty, 1), L.smem, P);
+      continue;
+    }
     // the three instantiations launch_box() chooses from on the device
     if (g_in_wdot) EMU_LAUNCH(true, false);
     else if (aux_in_gen) EMU_LAUNCH(false, true);

@@ -189,6 +189,22 @@ def test_emulated_strict_build_is_bit_identical_to_the_oracle(pkg, oracle_mod, p
             assert (a is None and b is None) or np.array_equal(a, b), (n, nchem, bcs)
 
 
+def test_emulated_bulk_copy_staging_variant(emu, oracle_mod, port):
+    """rhs_fused_kernel<..., STAGE> (EULERB200_STAGE=1, the TMA / bulk-copy A/B variant): interior tiles read the
+    species of the current plane from the shared-memory window filled by cp.async.bulk + mbarrier (emulated:
+    copy at issue, phase flip on the byte count).  Same bits as the default kernel: only where the values
+    are read from differs."""
+    for n, nchem, bcs in [((70, 40, 10), 10, [P] * 6), ((100, 26, 20), 2, [R, R, P, P, N, N]), ((40, 30, 9), 4, [N] * 6)]:
+        w = oracle_mod.random_state(n, nchem, seed=3 + sum(n))
+        d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+        ret0, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384)
+        ret1, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, stage=1)
+        assert ret0 == 0 and ret1 == 0
+        assert all(np.array_equal(a, b) for a, b in zip(base, got))
+        ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+        assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
+
+
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)
