@@ -147,8 +147,8 @@ struct eulerb200_ctx {
   ncclComm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_packed = nullptr, ev_recv = nullptr;
-  cudaStream_t slab_stream[2] = {nullptr, nullptr};      // boundary slabs run side by side
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaStream_t slab_stream[3] = {nullptr, nullptr, nullptr};      // boundary slabs run side by side (highest stream priority)
+  cudaEvent_t ev_fork = nullptr, ev_halo = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool exchange_open = false;
 
   // staging for eulerb200_rhs_host (allocated on first use)
@@ -158,7 +158,7 @@ struct eulerb200_ctx {
   static const int kMaxSlabs = 64;
   cudaEvent_t ev_up[kMaxSlabs], ev_done[kMaxSlabs];
   bool host_ready = false;
-  size_t max_smem_set[6][3][3] = {}, carveout_for[6][3][3] = {};   // per kernel instantiation [variant][kind][part]
+  size_t max_smem_set[2][6][3][3] = {}, carveout_for[2][6][3][3] = {};   // per kernel instantiation [xc][variant][kind][part]
   // eulerb200_profile: events T0 start, T1 after the pre-pass, T2 after the pack kernels, T3 after the interior
   // kernel, T4 after the wait for the halo, T5 end (stream s); C0 / C1 around the transfer (side stream)
   bool profile_on = false;
@@ -168,9 +168,15 @@ struct eulerb200_ctx {
   bool forcing_in_wdot = false;  // eulerb200_set_forcing_in_wdot
   long ctas_target = 5920;       // EULERB200_CTAS: CTAs a launch aims for when cutting z-segments (tuning)
   int force_kernel = 1;          // EULERB200_KERNEL=0: never use the AG instantiation for boundary-heavy launches
+  double ag_frac = 0.25;         // EULERB200_AG_FRAC: share of boundary tiles from which a launch takes the AG instantiation
   int variant = 0;
   int split = 0;                 // EULERB200_SPLIT=1: fluid fields and species in separate launches
   int stage = 0;                 // EULERB200_STAGE=1: the bulk-copy staging variant of the fused kernel (A/B)
+  int overlap = 1;               // EULERB200_OVERLAP: 1 interior launch behind the halo exchange, then the shell launches;
+                                 // 2 shells on high-priority streams as soon as the halo is in; 0 exchange first, one launch (rhs_impl)
+  bool prof_pack_first = false;
+  int xc = 1;                    // EULERB200_XC=0: 31-column tiles (default: tiles own all 32 columns, the closing x-faces come
+                                 // from the top warp; 59.2 vs 61.1 ms at 512^3 / NVAR 15)
   int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
   double* aux[4] = {nullptr, nullptr, nullptr, nullptr};   // per-cell 1/rho, p, c, sqrt(rho)
   bool use_aux = true;
@@ -193,8 +199,19 @@ struct KernelVariant {
   void (*fn[3][3])(const eb::RhsParams);
   int threads;
   const char* name;
+  // the XC instantiations of the same kinds and parts (rhs_fused_kernel<..., XC>), nullptr: not compiled
+  void (*fnx[3][3])(const eb::RhsParams);
 };
 #define EB_K(T, B, GW, AG, PART, TYC) eb::rhs_fused_kernel<T, B, GW, AG, eb::PART, TYC>
+#define EB_KX(T, B, GW, AG, PART, TYC) eb::rhs_fused_kernel<T, B, GW, AG, eb::PART, TYC, false, true>
+#define EB_NONE {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
+// (XC instantiations: the fused launch of each kind; the split launches keep the 31-column tiles)
+#ifdef EB_FAST_BUILD
+#define EB_XC_ALL(T, B, TYC) {{EB_KX(T, B, false, false, PART_ALL, TYC), nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
+#else
+#define EB_XC_ALL(T, B, TYC) {{EB_KX(T, B, false, false, PART_ALL, TYC), nullptr, nullptr}, {EB_KX(T, B, false, true, PART_ALL, TYC), nullptr, nullptr}, \
+                              {EB_KX(T, B, true, false, PART_ALL, TYC), nullptr, nullptr}}
+#endif
 #define EB_KIND(T, B, GW, AG, TYC) {EB_K(T, B, GW, AG, PART_ALL, TYC), EB_K(T, B, GW, AG, PART_FLUID, TYC), EB_K(T, B, GW, AG, PART_TRACERS, TYC)}
 #define EB_KERNELS_FULL(T, B, TYC) {EB_KIND(T, B, false, false, TYC), EB_KIND(T, B, false, true, TYC), EB_KIND(T, B, true, false, TYC)}
 #define EB_KERNELS_PLAIN(T, B, TYC) {EB_KIND(T, B, false, false, TYC), {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
@@ -204,14 +221,14 @@ struct KernelVariant {
 #define EB_KERNELS_FULL EB_KERNELS_PLAIN
 #endif
 const KernelVariant kVariants[] = {
-    {EB_KERNELS_PLAIN(256, 1, 8), 256, "256x1 (<=255 regs)"},
-    {EB_KERNELS_FULL(384, 1, 12), 384, "384x1 (<=168 regs)"},
-    {EB_KERNELS_FULL(512, 1, 16), 512, "512x1 (<=128 regs)"},
-    {EB_KERNELS_PLAIN(640, 1, 20), 640, "640x1 (<=96 regs)"},
-    {EB_KERNELS_FULL(384, 1, 0), 384, "any tile shape, <= 384 threads"},
+    {EB_KERNELS_PLAIN(256, 1, 8), 256, "256x1 (<=255 regs)", EB_NONE},
+    {EB_KERNELS_FULL(384, 1, 12), 384, "384x1 (<=168 regs)", EB_XC_ALL(384, 1, 12)},
+    {EB_KERNELS_FULL(512, 1, 16), 512, "512x1 (<=128 regs)", EB_NONE},      // (XC measured slower here: 28.4 vs 27.7 ms, RT 512^3)
+    {EB_KERNELS_PLAIN(640, 1, 20), 640, "640x1 (<=96 regs)", EB_NONE},
+    {EB_KERNELS_FULL(384, 1, 0), 384, "any tile shape, <= 384 threads", EB_NONE},
     // A/B variant (EULERB200_STAGE=1): species of the current plane staged in shared memory by cp.async.bulk
     {{{eb::rhs_fused_kernel<384, 1, false, false, eb::PART_ALL, 12, true>, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}},
-     384, "384x1, bulk-copy staging of the species plane"},
+     384, "384x1, bulk-copy staging of the species plane", EB_NONE},
 };
 const int kGenericVariant = 4;
 const int kStageVariant = 5;
@@ -292,11 +309,19 @@ int launch_part(eulerb200_ctx* c, eb::RhsParams P, int kind, int part, cudaStrea
     }
   }
   const KernelVariant& V = kVariants[vi];
-  void (*const fn)(const eb::RhsParams) = V.fn[kind][part];
+  void (*fn)(const eb::RhsParams) = V.fn[kind][part];
+  if (c->xc && V.fnx[kind][part] && vi != kStageVariant) {
+    // tiles of 32 owned columns (the launch keeps the compiled-in 32 x threads/32 shape: checked above)
+    const eb::LaunchGeom Lx = eb::launch_geom(P.lo, P.hi, nf, V.threads, c->pair_sync, c->ctas_target, 1);
+    if (Lx.xc && Lx.tx == L.tx && Lx.ty == L.ty && Lx.smem <= (size_t)227 * 1024) {
+      L = Lx;
+      fn = V.fnx[kind][part];
+    }
+  }
   P.seg_len = L.seg_len;
   P.pair_sync = L.pair;
-  size_t& smem_set = c->max_smem_set[vi][kind][part];
-  size_t& carve_for = c->carveout_for[vi][kind][part];
+  size_t& smem_set = c->max_smem_set[L.xc][vi][kind][part];
+  size_t& carve_for = c->carveout_for[L.xc][vi][kind][part];
   if (L.smem > smem_set) {
     EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
     smem_set = L.smem;
@@ -304,7 +329,12 @@ int launch_part(eulerb200_ctx* c, eb::RhsParams P, int kind, int part, cudaStrea
   if (L.smem != carve_for) {
     // the stencil loads live in L1: ask for the smallest shared-memory carve-out that holds one CTA
     // (+1 KB the system reserves per CTA) and leave the rest of the 256 KB to L1
-    const int pct = (int)std::min<size_t>(100, (100 * (L.smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+    // (the carve-outs sm_100 offers; asked for as floor(100 S / 228), the form the 132 KB one was measured with)
+    static const size_t kCarve[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    size_t pick = 228;
+    for (size_t q = 0; q < sizeof kCarve / sizeof kCarve[0]; q++)
+      if (kCarve[q] * 1024 >= L.smem + 1024) { pick = kCarve[q]; break; }
+    const int pct = (int)(100 * pick / 228);
     EB_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     carve_for = L.smem;
   }
@@ -326,8 +356,8 @@ int launch_box(eulerb200_ctx* c, eb::RhsParams P, const long lo[3], const long h
   int kind = 0;
   if (c->forcing_in_wdot) kind = 2;
   else if (c->force_kernel == 1 && c->use_aux) {
-    const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, 5 + P.nchem, kVariants[c->variant_part[0]].threads, c->pair_sync, c->ctas_target);
-    if (eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= 0.25) kind = 1;
+    const eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, 5 + P.nchem, kVariants[c->variant_part[0]].threads, c->pair_sync, c->ctas_target, c->xc);
+    if (eb::boundary_tile_fraction(P.lo, P.hi, P.nx, P.ny, L) >= c->ag_frac) kind = 1;
   }
   if (!kVariants[kGenericVariant].fn[kind][0]) {      // reduced builds (tuning, strict) compile the default kind only
     if (kind == 2) return fail(c, -1, "this build of the library has no hook-assigned-forcing instantiation");
@@ -388,7 +418,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
       if (!c->remote[f]) continue;
       const long nent = eb::face_len(c->cfg, f) / nv;
       double* dst = reinterpret_cast<double*>(c->peer_base[f] + c->peer_slab_off[f][par]);
-      eb::pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
+      eb::pack_face_kernel<<<(unsigned)((nent + 7) / 8), dim3(32, 8), 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
       halo_signal_kernel<<<1, 1, 0, c->comm_stream>>>(
           reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
       c->launches += 2;
@@ -404,7 +434,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
   for (int f = 0; f < 6; f++) {
     if (!c->remote[f]) continue;
     const long nent = eb::face_len(c->cfg, f) / nv;
-    eb::pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, s>>>(face_geom(c, f, w), c->send[f], nent);
+    eb::pack_face_kernel<<<(unsigned)((nent + 7) / 8), dim3(32, 8), 0, s>>>(face_geom(c, f, w), c->send[f], nent);
     c->launches++;
   }
   EB_CUDA(c, cudaGetLastError());
@@ -528,7 +558,9 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_VARIANT_T")) { const int v = atoi(ev); if (v >= 0 && v < kNumVariants) c->variant_part[2] = v; }
   if (const char* ev = getenv("EULERB200_SPLIT")) c->split = atoi(ev) != 0;
   if (const char* ev = getenv("EULERB200_STAGE")) c->stage = atoi(ev) != 0;
-  for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[a_][b_][d_] = (size_t)-1;
+  if (const char* ev = getenv("EULERB200_XC")) c->xc = atoi(ev) != 0;
+  if (const char* ev = getenv("EULERB200_OVERLAP")) c->overlap = std::max(0, std::min(2, atoi(ev)));
+  for (int x_ = 0; x_ < 2; x_++) for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[x_][a_][b_][d_] = (size_t)-1;
   if (cfg->device >= 0) {
     e = cudaSetDevice(cfg->device);
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
@@ -551,6 +583,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_NO_AUX")) c->use_aux = (atoi(ev) == 0);
   if (const char* ev = getenv("EULERB200_PAIR")) c->pair_sync = std::max(0, std::min(2, atoi(ev)));
   if (const char* ev = getenv("EULERB200_KERNEL")) c->force_kernel = (atoi(ev) != 0) ? 1 : 0;
+  if (const char* ev = getenv("EULERB200_AG_FRAC")) c->ag_frac = atof(ev);
   if (const char* ev = getenv("EULERB200_CTAS")) c->ctas_target = std::max(1L, atol(ev));
   if (const char* ev = getenv("EULERB200_CHEMT")) c->use_chemT = (atoi(ev) != 0);
   if (c->use_aux)
@@ -568,12 +601,19 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     }
   }
   if (c->any_remote) {
-    EB_CREATE(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    // The exchange stream and the shell streams get the highest priority: their kernels are small and the
+    // interior launch keeps every SM occupied (one 384-thread CTA holds the whole register file), so at
+    // equal priority the pack / NCCL copy CTAs are only scheduled when the interior grid runs dry -- the
+    // halo then arrives after 57 ms instead of 2 (timeline of profiles/r2_bench_n2.json).
+    int prio_least = 0, prio_greatest = 0;
+    EB_CREATE(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    EB_CREATE(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_greatest));
     EB_CREATE(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     EB_CREATE(cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming));
     EB_CREATE(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    for (int h = 0; h < 2; h++) {
-      EB_CREATE(cudaStreamCreateWithFlags(&c->slab_stream[h], cudaStreamNonBlocking));
+    EB_CREATE(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    for (int h = 0; h < 3; h++) {
+      EB_CREATE(cudaStreamCreateWithPriority(&c->slab_stream[h], cudaStreamNonBlocking, prio_greatest));
       EB_CREATE(cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming));
     }
   }
@@ -604,7 +644,8 @@ int eulerb200_destroy(eulerb200_ctx* c)
   if (c->ev_packed) cudaEventDestroy(c->ev_packed);
   if (c->ev_recv) cudaEventDestroy(c->ev_recv);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  for (int h = 0; h < 2; h++) {
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  for (int h = 0; h < 3; h++) {
     if (c->slab_stream[h]) cudaStreamDestroy(c->slab_stream[h]);
     if (c->ev_join[h]) cudaEventDestroy(c->ev_join[h]);
   }
@@ -777,9 +818,9 @@ static int profile_collect(eulerb200_ctx* c)
   EB_CUDA(c, cudaEventSynchronize(c->pev[5]));
   auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, c->pev[a], c->pev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0; } return (double)ms; };
   c->pacc[0] += el(0, 5);
-  c->pacc[1] += el(0, 1);
+  c->pacc[c->prof_pack_first ? 2 : 1] += el(0, 1);
   if (c->any_remote) {
-    c->pacc[2] += el(1, 2);
+    c->pacc[c->prof_pack_first ? 1 : 2] += el(1, 2);
     if (cudaEventSynchronize(c->pev[7]) == cudaSuccess) c->pacc[3] += el(6, 7);
     c->pacc[4] += el(2, 3);
     c->pacc[5] += el(3, 4);
@@ -807,25 +848,6 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     P.et_rw = const_cast<double*>(w[4]);
   }
   const long n[3] = {P.nx, P.ny, P.nz};
-  EB_PREC(c, 0, s);
-  {
-    int rc_ = launch_aux(c, P, 0, P.nz, s);
-    if (rc_) return rc_;
-  }
-  EB_PREC(c, 1, s);
-  if (!c->any_remote) {
-    const long lo[3] = {0, 0, 0};
-    int rc_ = launch_box(c, P, lo, n, s);
-    if (rc_) return rc_;
-    EB_PREC(c, 5, s);
-    return profile_collect(c);
-  }
-  // Overlap (the structure of utilities.cpp:61 -> 76-116 -> 119 -> 123-195): start the
-  // exchange, evaluate every cell whose stencils stay clear of the remote faces, wait for
-  // the halos, then evaluate the remaining shell as non-overlapping slabs.
-  int rc = exchange_start(c, w, s);
-  if (rc) return rc;
-  for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
   long lo[3], hi[3];
   bool interior = true;
   for (int d = 0; d < 3; d++) {
@@ -833,15 +855,86 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     hi[d] = n[d] - (c->remote[2 * d + 1] ? 3 : 0);
     if (hi[d] <= lo[d]) interior = false;
   }
-  EB_PREC(c, 2, s);
-  if (!interior) {
+  int rc;
+  if (c->any_remote && (!c->overlap || !interior)) {
+    // Exchange first: pack, send / receive the halo slabs while the pre-pass runs, wait, then ONE launch
+    // over the whole box (boundary tiles read the slabs).  The slabs of a 512^3 box are 94 MB per face
+    // -- a few hundred microseconds over NVLink -- against a 60 ms kernel, so hiding them behind an
+    // interior launch buys less than the six shell launches and the smaller interior grid cost
+    // (profiles/README.md, 8 GPUs).  EULERB200_OVERLAP=1 restores the interior / shell schedule.
+    // (slow mode: the pre-pass rebuilds the total energy the pack reads, so it goes first)
+    c->prof_pack_first = !slow_mode;
+    EB_PREC(c, 0, s);
+    if (slow_mode && (rc = launch_aux(c, P, 0, P.nz, s))) return rc;
+    if (slow_mode) EB_PREC(c, 1, s);
+    if ((rc = exchange_start(c, w, s))) return rc;
+    for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
+    if (!slow_mode) EB_PREC(c, 1, s);
+    if (!slow_mode && (rc = launch_aux(c, P, 0, P.nz, s))) return rc;
+    EB_PREC(c, 2, s);
     EB_PREC(c, 3, s);
-    rc = exchange_end(c, s);
-    if (rc) return rc;
+    if ((rc = exchange_end(c, s))) return rc;
     EB_PREC(c, 4, s);
     const long z[3] = {0, 0, 0};
-    rc = launch_box(c, P, z, n, s);
+    if ((rc = launch_box(c, P, z, n, s))) return rc;
+    EB_PREC(c, 5, s);
+    return profile_collect(c);
+  }
+  c->prof_pack_first = false;
+  EB_PREC(c, 0, s);
+  {
+    int rc_ = launch_aux(c, P, 0, P.nz, s);
+    if (rc_) return rc_;
+  }
+  EB_PREC(c, 1, s);
+  if (!c->any_remote) {
+    const long lo0[3] = {0, 0, 0};
+    int rc_ = launch_box(c, P, lo0, n, s);
+    if (rc_) return rc_;
+    EB_PREC(c, 5, s);
+    return profile_collect(c);
+  }
+  // Overlap (the structure of utilities.cpp:61 -> 76-116 -> 119 -> 123-195): start the
+  // exchange, evaluate every cell whose stencils stay clear of the remote faces, wait for
+  // the halos, then evaluate the remaining shell as non-overlapping slabs.
+  rc = exchange_start(c, w, s);
+  if (rc) return rc;
+  for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
+  EB_PREC(c, 2, s);
+  const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low
+  const long b0[3] = {0, 0, hi[2]}, b1[3] = {n[0], n[1], n[2]};                 // z-high
+  const long c0[3] = {0, 0, lo[2]}, c1[3] = {n[0], lo[1], hi[2]};               // y-low
+  const long d0[3] = {0, hi[1], lo[2]}, d1[3] = {n[0], n[1], hi[2]};            // y-high
+  const long e0[3] = {0, lo[1], lo[2]}, e1[3] = {lo[0], hi[1], hi[2]};          // x-low
+  const long f0[3] = {hi[0], lo[1], lo[2]}, f1[3] = {n[0], hi[1], hi[2]};       // x-high
+  const long* box[6][2] = {{a0, a1}, {b0, b1}, {c0, c1}, {d0, d1}, {e0, e1}, {f0, f1}};
+  if (c->overlap == 2) {
+    // Early shells: the slabs do not depend on the interior launch, only on the pre-pass (per-cell arrays)
+    // and on the halo.  They go to three high-priority streams that wait for exactly those two, so their
+    // CTAs slip into the SMs as interior CTAs retire -- a few milliseconds into the interior launch --
+    // instead of running as a sparsely filled tail after it.
+    EB_CUDA(c, cudaEventRecord(c->ev_fork, s));                      // pre-pass (and the NCCL-path pack) done
+    rc = launch_box(c, P, lo, hi, s);                                // interior first: it starts at once
     if (rc) return rc;
+    EB_PREC(c, 3, s);
+    EB_PREC(c, 4, s);
+    for (int h = 0; h < 3; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_fork, 0));
+    rc = exchange_end(c, c->slab_stream[0]);
+    if (rc) return rc;
+    EB_CUDA(c, cudaEventRecord(c->ev_halo, c->slab_stream[0]));
+    for (int h = 1; h < 3; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_halo, 0));
+    int q = 0;
+    for (int b = 0; b < 6; b++) {
+      bool empty = false;
+      for (int d = 0; d < 3; d++) if (box[b][1][d] <= box[b][0][d]) empty = true;
+      if (empty) continue;
+      if ((rc = launch_box(c, P, box[b][0], box[b][1], c->slab_stream[q % 3]))) return rc;
+      q++;
+    }
+    for (int h = 0; h < 3; h++) {
+      EB_CUDA(c, cudaEventRecord(c->ev_join[h], c->slab_stream[h]));
+      EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[h], 0));
+    }
     EB_PREC(c, 5, s);
     return profile_collect(c);
   }
@@ -852,15 +945,8 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
   if (rc) return rc;
   EB_PREC(c, 4, s);
   {
-    const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low
-    const long b0[3] = {0, 0, hi[2]}, b1[3] = {n[0], n[1], n[2]};                 // z-high
-    const long c0[3] = {0, 0, lo[2]}, c1[3] = {n[0], lo[1], hi[2]};               // y-low
-    const long d0[3] = {0, hi[1], lo[2]}, d1[3] = {n[0], n[1], hi[2]};            // y-high
-    const long e0[3] = {0, lo[1], lo[2]}, e1[3] = {lo[0], hi[1], hi[2]};          // x-low
-    const long f0[3] = {hi[0], lo[1], lo[2]}, f1[3] = {n[0], hi[1], hi[2]};       // x-high
     // the slabs are independent and individually too small to fill the GPU: spread them over the
     // compute stream and two helper streams, then join
-    const long* box[6][2] = {{a0, a1}, {b0, b1}, {c0, c1}, {d0, d1}, {e0, e1}, {f0, f1}};
     cudaStream_t lane[3] = {s, c->slab_stream[0], c->slab_stream[1]};
     EB_CUDA(c, cudaEventRecord(c->ev_fork, s));
     for (int h = 0; h < 2; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_fork, 0));

@@ -41,19 +41,22 @@ EB_HD long face_cell(const FaceGeom& g, long src, long a, long b)
 // What this rank sends through face f: its three layers nearest that face in increasing
 // index order, all NVAR values of a cell contiguous (euler3D.hpp:644-786).
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
+// Launch with blocks of 32 x 8 threads: a warp (threadIdx.y) packs one entry, its lanes the NVAR values
+// of that cell, so that every store instruction writes one contiguous run of the destination -- which
+// matters when the destination is the neighbour's slab across NVLink (peer-store transport: a
+// thread-per-entry kernel issues NVAR scattered 8-byte remote stores per thread; measured 38 GB/s).
 __global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
 {
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
-  int d; long a, b, na;
-  face_decode(g, e, d, a, b, na);
-  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
-  const long src = (g.f % 2 == 0) ? d : n - 3 + d;
-  const long cell = face_cell(g, src, a, b);
   const int nv = 5 + g.nchem;
-  double* o = buf + (long)nv * e;
-#pragma unroll
-  for (int v = 0; v < 5; v++) o[v] = g.w[v][cell];
-  for (int v = 0; v < g.nchem; v++) o[5 + v] = g.w[5][cell * g.nchem + v];
+  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
+  for (long e = blockIdx.x * (long)blockDim.y + threadIdx.y; e < nent; e += (long)gridDim.x * blockDim.y) {
+    int d; long a, b, na;
+    face_decode(g, e, d, a, b, na);
+    const long src = (g.f % 2 == 0) ? d : n - 3 + d;
+    const long cell = face_cell(g, src, a, b);
+    double* o = buf + (long)nv * e;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x)
+      o[v] = (v < 5) ? g.w[v][cell] : g.w[5][cell * g.nchem + (v - 5)];
   }
 }
 

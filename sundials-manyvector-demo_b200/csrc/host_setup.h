@@ -4,6 +4,7 @@
 // include it too).
 // ---------------------------------------------------------------------------
 #pragma once
+#include <cmath>
 #include <stdint.h>
 #include <algorithm>
 #include <vector>
@@ -137,14 +138,16 @@ struct LaunchGeom {
   int seg_len;
   size_t smem;
   int pair;          // 0: CTA-wide barriers, 1: row rendezvous + two FY buffers, 2: row rendezvous twice per plane
+  int xc;            // tiles own all tx columns; the closing x-face column comes from the top warp (rhs_fused_kernel<..., XC>)
 };
 
 // Tile shape: 256 threads; a full warp along x whenever the box is at least 31 cells
 // wide, otherwise the narrowest power of two that holds extent+1 faces (thin boxes such
 // as the 3-cell-wide hurricane plane then put the threads along y).
 // nf: fields the launch evaluates (NVAR for the fused launch, 5 / nchem for the fluid / species launches)
+// want_xc: tiles of tx owned columns (rhs_fused_kernel<..., XC>) where rows are warps
 inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nf, int threads = 256, int want_pair = 0,
-                              long ctas_target = 5920)
+                              long ctas_target = 5920, int want_xc = 0)
 {
   LaunchGeom L;
   const long ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -158,13 +161,29 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nf, int th
   const size_t smem_max = (size_t)227 * 1024, per_row = (size_t)nf * tx * sizeof(double);
   while (ty > 2 && per_row * (3 * ty - 2) > smem_max) ty--;
   L.tx = tx; L.ty = ty;
-  L.gx = (unsigned)((ex + tx - 2) / (tx - 1));
+  L.xc = (want_xc && tx == 32 && ty >= 2) ? 1 : 0;
+  L.gx = L.xc ? (unsigned)((ex + tx - 1) / tx) : (unsigned)((ex + tx - 2) / (tx - 1));
   L.gy = (unsigned)((ey + ty - 2) / (ty - 1));
   // z-segments: enough CTAs for ~20 waves on 148 SMs x 2 resident CTAs (ctas_target; tuning knob
   // EULERB200_CTAS), but at least 8 cells per segment (one extra z-face is computed per segment)
   const long tiles = (long)L.gx * L.gy;
   long nseg = (ctas_target + tiles - 1) / tiles;
   nseg = std::max(1L, std::min(nseg, (ez + 7) / 8));
+  {
+    // around that count, the one that wastes least: the last wave of CTAs on the 148 SMs (one CTA per SM)
+    // is only partly filled, and every segment computes one z-face more than it has planes
+    // (512^3, 16 x 47 tiles: 12 segments = 60.97 waves instead of 8 = 40.65; measured 59.0 vs 59.2 ms)
+    const double sms = 148.0;
+    double best = 1e300;
+    long pick = nseg;
+    for (long g = std::max(1L, nseg / 2); g <= std::min(2 * nseg, (ez + 7) / 8); g++) {
+      const long seg = (ez + g - 1) / g, gz = (ez + seg - 1) / seg;
+      const double ideal = (double)(tiles * gz) / sms;
+      const double cost = std::ceil(ideal) / ideal * (1.0 + 1.0 / (3.0 * (double)seg));
+      if (cost < best - 1e-12) { best = cost; pick = g; }
+    }
+    nseg = pick;
+  }
   L.seg_len = (int)((ez + nseg - 1) / nseg);
   L.gz = (unsigned)((ez + L.seg_len - 1) / L.seg_len);
   // pairwise row rendezvous (rhs_fused_kernel): rows must be warps, one named barrier per row
@@ -172,6 +191,9 @@ inline LaunchGeom launch_geom(const long lo[3], const long hi[3], int nf, int th
   L.pair = (tx == 32 && ty >= 2 && ty <= 16) ? want_pair : 0;
   if (L.pair == 1 && per_row * (4 * ty - 2) > smem_max) L.pair = 2;
   L.smem = per_row * ((L.pair == 1 ? 4 : 3) * ty - 2);
+  // XC: two more slots per FX row (the face column of the top warp, double-buffered) and the four mbarriers
+  // of its hand-over
+  if (L.xc) L.smem += (size_t)nf * 2 * (ty - 1) * sizeof(double) + 32;
   return L;
 }
 
@@ -181,9 +203,10 @@ inline double boundary_tile_fraction(const long lo[3], const long hi[3], long nx
 {
   (void)hi;
   long okx = 0, oky = 0;
+  const int px = L.xc ? L.tx : L.tx - 1;           // columns a tile owns
   for (unsigned b = 0; b < L.gx; b++) {
-    const long t0 = lo[0] + (long)b * (L.tx - 1);
-    if (!(t0 - 3 < 0 || t0 + L.tx - 1 + 2 >= nx)) okx++;
+    const long t0 = lo[0] + (long)b * px;
+    if (!(t0 - 3 < 0 || t0 + px + 2 >= nx)) okx++;
   }
   for (unsigned b = 0; b < L.gy; b++) {
     const long t0 = lo[1] + (long)b * (L.ty - 1);

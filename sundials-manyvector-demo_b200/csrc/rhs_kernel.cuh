@@ -420,10 +420,14 @@ struct EmitSlot {
 };
 // (2) the flux through the z-face above the cell closes the divergence of its field (sum order of
 // utilities.cpp:202-207) and the result goes out to wdot; a species pair as one 16-byte store
-template <bool GW, int TRc, int Tc>
+// (TRXc: stride of FX where it differs from ZLO's; XU: the flux through the upper x-face is read through the
+// separate pointer FXU instead of from the next slot, rhs_fused_kernel<..., XC>)
+template <bool GW, int TRc, int Tc, int TRXc = TRc, bool XU = false>
 struct EmitDiv {
   const RhsParams& P;
   double* FX;
+  const double* FXU;
+  const double* fxu;
   double* FY;
   double* ZLO;
   int rTR, rT, TX;
@@ -431,14 +435,15 @@ struct EmitDiv {
   double *fx, *fy, *zl, *dst;    // running pointers of the species part
   bool fast;                     // species pairs: plain 16-byte stores
   EB_HD int TR() const { return TRc > 0 ? TRc : rTR; }
+  EB_HD int TRX() const { return TRXc > 0 ? TRXc : rTR; }
   EB_HD int T() const { return Tc > 0 ? Tc : rT; }
   EB_HD double close(int v, double zup) const
   {
 #if defined(EB_STRICT) || defined(EB_TRUE_DIVISION)
-    const double div = ((FX[v * TR() + 1] - FX[v * TR()]) / P.dx + (FY[v * T() + TX] - FY[v * T()]) / P.dy)
+    const double div = (((XU ? FXU[v * TRX()] : FX[v * TRX() + 1]) - FX[v * TRX()]) / P.dx + (FY[v * T() + TX] - FY[v * T()]) / P.dy)
                        + (zup - ZLO[v * TR()]) / P.dz;
 #else
-    const double div = ((FX[v * TR() + 1] - FX[v * TR()]) * P.rdx + (FY[v * T() + TX] - FY[v * T()]) * P.rdy)
+    const double div = (((XU ? FXU[v * TRX()] : FX[v * TRX() + 1]) - FX[v * TRX()]) * P.rdx + (FY[v * T() + TX] - FY[v * T()]) * P.rdy)
                        + (zup - ZLO[v * TR()]) * P.rdz;
 #endif
     ZLO[v * TR()] = zup;
@@ -453,17 +458,18 @@ struct EmitDiv {
   EB_HD void operator()(int v, double zup) const { store(v, close(v, zup)); }
   EB_HD void species_begin()
   {
-    fx = FX + 5 * TR(); fy = FY + 5 * T(); zl = ZLO + 5 * TR();
+    fx = FX + 5 * TRX(); fy = FY + 5 * T(); zl = ZLO + 5 * TR();
+    if (XU) fxu = FXU + 5 * TRX();
     dst = P.wdot[5] + cell * P.nchem;
     fast = !GW && P.vec_store;
   }
   EB_HD double close_next(int q, double zup) const      // q-th species (0 / 1) at the running pointers
   {
 #if defined(EB_STRICT) || defined(EB_TRUE_DIVISION)
-    return ((fx[q * TR() + 1] - fx[q * TR()]) / P.dx + (fy[q * T() + TX] - fy[q * T()]) / P.dy)
+    return (((XU ? fxu[q * TRX()] : fx[q * TRX() + 1]) - fx[q * TRX()]) / P.dx + (fy[q * T() + TX] - fy[q * T()]) / P.dy)
            + (zup - zl[q * TR()]) / P.dz;
 #else
-    return ((fx[q * TR() + 1] - fx[q * TR()]) * P.rdx + (fy[q * T() + TX] - fy[q * T()]) * P.rdy)
+    return (((XU ? fxu[q * TRX()] : fx[q * TRX() + 1]) - fx[q * TRX()]) * P.rdx + (fy[q * T() + TX] - fy[q * T()]) * P.rdy)
            + (zup - zl[q * TR()]) * P.rdz;
 #endif
   }
@@ -483,7 +489,8 @@ struct EmitDiv {
         st_out(dst + 1, (GW ? dst[1] : 0.0) - db);
       }
     }
-    fx += 2 * TR(); fy += 2 * T(); zl += 2 * TR(); dst += 2;
+    fx += 2 * TRX(); fy += 2 * T(); zl += 2 * TR(); dst += 2;
+    if (XU) fxu += 2 * TRX();
   }
 };
 
@@ -581,16 +588,20 @@ __device__ __forceinline__ void eb_bulk_g2s(void* dst_smem, const void* src_gmem
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(eb_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(eb_smem_addr(bar)) : "memory");
 }
+__device__ __forceinline__ void eb_mbar_arrive(unsigned long long* bar)      // release.cta
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(eb_smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void eb_mbar_wait(unsigned long long* bar, unsigned parity)
 {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "EB_WAIT:\n"
+      "EB_WAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra EB_DONE;\n"
-      "bra EB_WAIT;\n"
-      "EB_DONE:\n"
+      "@p bra EB_DONE_%=;\n"
+      "bra EB_WAIT_%=;\n"
+      "EB_DONE_%=:\n"
       "}\n" ::"r"(eb_smem_addr(bar)), "r"(parity) : "memory");
 }
 #endif
@@ -624,12 +635,14 @@ __device__ __forceinline__ void eb_mbar_wait(unsigned long long* bar, unsigned p
 // while the z-faces of plane k are computed; the x- and y-face species loops then read shared memory
 // (16-byte loads at stride 8 nchem B: conflict-free per quarter warp for nchem = 10) instead of 19
 // cache lines per load.  The z-stencil (six planes) cannot be staged: 6 x tile x 8 nchem B = 184 KB.
-template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL, int TYC = 0, bool STAGE = false>
+template <int MAXT, int MINB, bool GW = false, bool AG = false, int PART = PART_ALL, int TYC = 0, bool STAGE = false, bool XC = false>
 __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P)
 {
+  static_assert(!XC || (TYC > 1 && !STAGE), "XC needs a compiled-in tile of 32 x TYC threads");
   EB_DYN_SMEM(double, smem);
   const int TX = TYC > 0 ? 32 : (int)blockDim.x, TY = TYC > 0 ? TYC : (int)blockDim.y, T = TX * TY;
   constexpr int Tc = 32 * TYC, TRc = TYC > 0 ? 32 * (TYC - 1) : 0;
+  constexpr int TRXc = XC ? 34 * (TYC - 1) : TRc;        // XC: FX rows carry two more slots, the face column of the top warp (two buffers)
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
   // fields of this launch: v0 .. v0+nf-1 in the reference's order
   const int v0 = (PART == PART_TRACERS) ? 5 : 0;
@@ -638,27 +651,50 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   const bool two_fy = !STAGE && P.pair_sync == 1;
   // the face-only top row of the tile never touches FX / ZLO: those arrays are [NF][TR]
   const int TR = T - TX;
-  double* FX = smem + t - (long)v0 * TR;               // indexed with the global field number v
-  double* FY = smem + (long)nf * TR + t - (long)v0 * T;
-  long fy_flip = two_fy ? (long)nf * T : 0;         // signed distance to the other FY buffer
-  double* ZLO = smem + (long)nf * (TR + (two_fy ? 2L : 1L) * T) + t - (long)v0 * TR;
+  const int TRX = XC ? TRXc : TR;
 
   const int nx = (int)P.nx, ny = (int)P.ny, nz = (int)P.nz;
   const int hix = (int)P.hi[0], hiy = (int)P.hi[1], hiz = (int)P.hi[2];
-  const int ti0 = (int)P.lo[0] + (int)blockIdx.x * (TX - 1);
+  const int ti0 = (int)P.lo[0] + (int)blockIdx.x * (XC ? TX : TX - 1);
   const int tj0 = (int)P.lo[1] + (int)blockIdx.y * (TY - 1);
   const int i = ti0 + tx, j = tj0 + ty;
   const int k0 = (int)P.lo[2] + (int)blockIdx.z * P.seg_len;
   const int k1 = (k0 + P.seg_len < hiz) ? k0 + P.seg_len : hiz;
 
   const bool row_ok = (ty < TY - 1) && (j < hiy);
-  const bool col_ok = (tx < TX - 1) && (i < hix);
+  const bool col_ok = (XC || tx < TX - 1) && (i < hix);
   const bool owns = row_ok && col_ok;                 // this thread owns a cell column
-  const bool need_x = row_ok && (i <= hix);           // lower x-face at position i
+  bool need_x = row_ok && (i <= hix);                 // lower x-face at position i
   const bool need_y = col_ok && (j <= hiy);           // lower y-face at position j
 
+  // XC: the tile owns all 32 columns; the x-faces that close it on the right (position ti0 + 32,
+  // rows 0 .. TY-2) are computed by lanes 0 .. TY-2 of the top warp -- whose own row only supplies
+  // y-faces -- into slot 32 + b of each FX row, b = plane parity (a tile cut short by the box closes
+  // itself: the lane at i == hix computes that face as before).  The top warp works one plane ahead
+  // of the rows (the loop starts one step early for it) and hands each column over through a pair of
+  // mbarriers per buffer (xfull[b]: column written; xfree[b]: every row has consumed it), so that
+  // neither side normally waits and the rows stay as loosely coupled as the row rendezvous leaves them.
+  const bool top = XC && ty == TY - 1;
+  const bool xc_tile = XC && (ti0 + TX <= hix);        // CTA-uniform
+  int xi = i, xj = j, xslot = XC ? ty * 34 + tx : t;
+  if (top) {
+    xi = ti0 + TX; xj = tj0 + tx;
+    need_x = xc_tile && tx < TY - 1 && xj < hiy;
+    xslot = (tx < TY - 1 ? tx : 0) * 34 + 32;
+  }
+  double* FX = smem + xslot - (long)v0 * TRX;           // indexed with the global field number v
+  double* FY = smem + (long)nf * TRX + t - (long)v0 * T;
+  long fy_flip = two_fy ? (long)nf * T : 0;         // signed distance to the other FY buffer
+  double* ZLO = smem + (long)nf * (TRX + (two_fy ? 2L : 1L) * T) + t - (long)v0 * TR;
+  unsigned long long* xfull = reinterpret_cast<unsigned long long*>(smem + (long)nf * (TRX + (two_fy ? 2L : 1L) * T + TR));
+  unsigned long long* xfree = xfull + 2;
+  if (XC) {
+    if (t == 0) { eb_mbar_init(xfull, 1); eb_mbar_init(xfull + 1, 1); eb_mbar_init(xfree, TY - 1); eb_mbar_init(xfree + 1, TY - 1); }
+    __syncthreads();
+  }
+
   // CTA-uniform: does any stencil of this tile reach beyond the owned range in x / y?
-  const bool gen_x = (ti0 - 3 < 0) || (ti0 + TX - 1 + 2 >= nx);
+  const bool gen_x = (ti0 - 3 < 0) || (ti0 + (XC ? TX : TX - 1) + 2 >= nx);
   const bool gen_y = (tj0 - 3 < 0) || (tj0 + TY - 1 + 2 >= ny);
 
   int mask = 0;
@@ -693,7 +729,10 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
   if (owns)
     face_dispatch<AG, PART>(k0 - 3 < 0 || k0 + 2 >= nz, P, 2, i, j, k0, EmitSlot<TRc>{ZLO, TR, nullptr});
 
-  for (int k = k0; k < k1; k++) {
+  for (int k = XC ? k0 - 1 : k0; k < k1; k++) {
+    // (XC: in the leading step k0 - 1 only the top warp works -- the face column of plane k0)
+    const bool act = !XC || k >= k0;
+    const int xn = k - k0;                                 // XC: plane number within the segment
     // ---- phase A: lower x- and y-faces of plane k -> shared memory ----
     if (STAGE && staged) {
       eb_mbar_wait(mbar, sphase);                          // plane k has landed
@@ -707,6 +746,33 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
       if (need_y)
         face_all<false, AG, PART, EmitSlot<Tc>, true>(P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr},
                                                       stage + (ty * SW + tx + 3) * npf, SW * npf);
+    } else if (XC) {
+      // y-faces first: they are all the row rendezvous publishes (FX stays inside the warp, or comes
+      // from the top warp through xfull)
+      if (act && need_y)
+        face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr});
+      if (pair) {
+        if (ty > 0) eb_bar_sync(ty, 64);
+        if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
+      } else {
+        __syncthreads();
+      }
+      // x-faces, one call site for both kinds of warp.  Rows: plane k.  Top warp: the column of plane k + 1
+      // (number xn + 1) into buffer (xn + 1) & 1, once the rows are done with the column of plane k - 1 there.
+      const int n1 = xn + 1;
+      const bool tcol = top && xc_tile && k + 1 < k1;
+      if (tcol && n1 >= 2) eb_mbar_wait(xfree + (n1 & 1), (unsigned)((n1 >> 1) - 1) & 1u);
+      if (top ? (tcol && need_x) : (act && need_x)) {
+        const int bits = face_dispatch<AG, PART>(gen_x, P, 0, xi, xj, top ? k + 1 : k,
+                                                 EmitSlot<TRXc>{top ? FX + (n1 & 1) : FX, TRX, nullptr});
+        if (owns) mask |= bits;
+      }
+      __syncwarp();                                        // FX of the warp's own lanes
+      if (tcol) {
+        if (tx == 0) eb_mbar_arrive(xfull + (n1 & 1));
+      } else if (!top && act && xc_tile) {
+        eb_mbar_wait(xfull + (xn & 1), (unsigned)(xn >> 1) & 1u);
+      }
     } else {
     if (need_x) {
       const int bits = face_dispatch<AG, PART>(gen_x, P, 0, i, j, k, EmitSlot<TRc>{FX, TR, nullptr});
@@ -715,7 +781,8 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
     if (need_y)
       face_dispatch<AG, PART>(gen_y, P, 1, i, j, k, EmitSlot<Tc>{FY, T, nullptr});
     }
-    if (EB_ABLATE & 1) {
+    if (XC) {
+    } else if (EB_ABLATE & 1) {
     } else if (pair) {
       if (ty > 0) eb_bar_sync(ty, 64);
       if (ty < TY - 1) eb_bar_sync(ty + 1, 64);
@@ -729,10 +796,16 @@ __global__ void __launch_bounds__(MAXT, MINB) rhs_fused_kernel(const RhsParams P
 
     // ---- phase B: z-face above cell (i,j,k); each flux closes the divergence of its
     //      field as soon as it exists (sum order of utilities.cpp:202-207) ----
-    if (owns) {
+    if (owns && act) {
       const long cell = i + nx * (j + ny * k);
+      // (XC: lane 31 finds the flux through its upper x-face in the column slot of this plane's parity)
+      const double* FXU = FX + ((XC && tx == TX - 1 && xc_tile) ? 1 + (xn & 1) : 1);
       face_dispatch<AG, PART>(k + 1 - 3 < 0 || k + 1 + 2 >= nz, P, 2, i, j, k + 1,
-                              EmitDiv<GW, TRc, Tc>{P, FX, FY, ZLO, TR, T, TX, cell, nullptr, nullptr, nullptr, nullptr, false});
+                              EmitDiv<GW, TRc, Tc, TRXc, XC>{P, FX, FXU, nullptr, FY, ZLO, TR, T, TX, cell, nullptr, nullptr, nullptr, nullptr, false});
+    }
+    if (XC && xc_tile && !top && act) {     // this row is done with the column of plane k
+      __syncwarp();
+      if (tx == 0) eb_mbar_arrive(xfree + (xn & 1));
     }
     if (EB_ABLATE & 1) {
     } else if (two_fy) {

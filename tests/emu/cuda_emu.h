@@ -158,16 +158,30 @@ inline void __syncwarp()
 }
 // cp.async.bulk + mbarrier (rhs_fused_kernel<..., STAGE>): the copy happens at issue; the barrier's
 // phase flips when the expected bytes have arrived; a waiting fibre yields until then.
-struct EmuMbar { unsigned phase; long pending; };
+// (arrive-count barriers of rhs_fused_kernel<..., XC>: the phase flips when `count` arrivals are in and no
+// bytes are outstanding.)  Eight bytes, like the hardware's.
+struct EmuMbar { unsigned char phase, count, arrived, pad; int pending; };
+static_assert(sizeof(EmuMbar) == 8, "an mbarrier is one 64-bit word");
 inline EmuMbar* emu_mbar(unsigned long long* bar) { return reinterpret_cast<EmuMbar*>(bar); }
-inline void eb_mbar_init(unsigned long long* bar, int) { emu_mbar(bar)->phase = 0; emu_mbar(bar)->pending = 0; }
-inline void eb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu_mbar(bar)->pending += bytes; }
+inline void emu_mbar_check(EmuMbar* m) { if (m->arrived >= m->count && m->pending == 0) { m->phase ^= 1u; m->arrived = 0; } }
+inline void eb_mbar_init(unsigned long long* bar, int count)
+{
+  EmuMbar* m = emu_mbar(bar);
+  m->phase = 0; m->count = (unsigned char)count; m->arrived = 0; m->pad = 0; m->pending = 0;
+}
+inline void eb_mbar_expect_tx(unsigned long long* bar, unsigned bytes)      // (arrive.expect_tx)
+{
+  EmuMbar* m = emu_mbar(bar);
+  m->pending += (int)bytes; m->arrived++;
+  emu_mbar_check(m);
+}
+inline void eb_mbar_arrive(unsigned long long* bar) { EmuMbar* m = emu_mbar(bar); m->arrived++; emu_mbar_check(m); }
 inline void eb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
 {
   memcpy(dst, src, bytes);
   EmuMbar* m = emu_mbar(bar);
-  m->pending -= bytes;
-  if (m->pending == 0) m->phase ^= 1u;
+  m->pending -= (int)bytes;
+  emu_mbar_check(m);
 }
 inline void eb_mbar_wait(unsigned long long* bar, unsigned parity)
 {

@@ -66,7 +66,7 @@ class Emu:
         return out
 
     def rhs(self, n, nchem, d, gamma, bcs, nbr, rank, w, forcing=None, recv=None, lo=None, hi=None, threads=256,
-            use_aux=1, energy_units=0.0, pair=0, g_in_wdot=None, aux_in_gen=0, split=0, chemT=0, stage=0):
+            use_aux=1, energy_units=0.0, pair=0, g_in_wdot=None, aux_in_gen=0, split=0, chemT=0, stage=0, xc=0):
         c = self.pkg.Config()
         c.nxl, c.nyl, c.nzl = n
         c.nchem, c.device = nchem, -1
@@ -83,5 +83,5 @@ class Emu:
         bits = C.c_int(0)
         L3 = C.c_long * 3
         ret = self.lib.emu_rhs(C.byref(c), _ptrs(w), _ptrs(out), _ptrs(recv) if recv is not None else None,
-                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair, 0 if g_in_wdot is None else 1, aux_in_gen, split, chemT, stage)
+                               C.byref(bits), L3(*lo) if lo else None, L3(*hi) if hi else None, threads, use_aux, C.c_double(energy_units), pair, 0 if g_in_wdot is None else 1, aux_in_gen, split, chemT, stage, xc)
         return ret, out, bits.value

@@ -17,7 +17,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT, int stage);
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT, int stage, int xc);
 
 extern "C" double emu_max_wavespeed(const double* const* w, long N, double gamma);
 extern "C" void emu_lincomb(int nterms, const double* coef, const double* const* x, double* out, long n);
@@ -40,7 +40,7 @@ int eulerb200_set_forcing_in_wdot(eulerb200_ctx* c, int32_t on) { if (!c) return
 int eulerb200_rhs_any(eulerb200_ctx* c, double, const double* const* w, double* const* wdot, void*)
 {
   int bits = 0;
-  const int rc = emu_rhs(&c->cfg, w, wdot, nullptr, &bits, nullptr, nullptr, 128, 1, 0.0, 0, c->gw ? 1 : 0, 1, getenv("EULERB200_SPLIT") ? atoi(getenv("EULERB200_SPLIT")) : 0, 0, 0);
+  const int rc = emu_rhs(&c->cfg, w, wdot, nullptr, &bits, nullptr, nullptr, 128, 1, 0.0, 0, c->gw ? 1 : 0, 1, getenv("EULERB200_SPLIT") ? atoi(getenv("EULERB200_SPLIT")) : 0, 0, 0, getenv("EULERB200_XC") ? atoi(getenv("EULERB200_XC")) : 1);
   if (rc) c->err = "STATE_ERROR: legal_state (fEuler) failed with flag = " + std::to_string(bits);
   return rc;
 }

@@ -10,7 +10,7 @@
 
 extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, double* const* wdot,
                        const double* const* recv, int* state_bits, const long* lo, const long* hi,
-                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT, int stage)
+                       int threads, int use_aux, double energy_units, int pair, int g_in_wdot, int aux_in_gen, int split, int use_chemT, int stage, int xc)
 {
   eb::RhsParams P;
   std::vector<double> aux[4];
@@ -56,21 +56,26 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
     const int part = parts[q];
     const int nf = part == eb::PART_ALL ? 5 + P.nchem : (part == eb::PART_FLUID ? 5 : P.nchem);
     eb::LaunchGeom L = eb::launch_geom(P.lo, P.hi, nf, threads, pair);
+    // the XC instantiations exist for the compiled-in tile shapes only (launch_part())
+    if (xc && L.tx == 32 && (L.ty == 12 || L.ty == 4)) L = eb::launch_geom(P.lo, P.hi, nf, threads, pair, 5920, 1);
     P.pair_sync = L.pair;
     if (pair != 0 && !L.pair) return -77;           // rows are not warps: the pairwise path does not apply
     P.seg_len = L.seg_len;
     const dim3 grid(L.gx, L.gy, L.gz), block(L.tx, L.ty, 1);
-#define EMU_PARTS(GW, AG, TYC)                                                                                         \
+#define EMU_PARTS_X(GW, AG, TYC, XC)                                                                                   \
     do {                                                                                                              \
-      if (part == eb::PART_ALL) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_ALL, TYC>, grid, block, L.smem, P);      \
-      else if (part == eb::PART_FLUID) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_FLUID, TYC>, grid, block, L.smem, P); \
-      else cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_TRACERS, TYC>, grid, block, L.smem, P);                \
+      if (part == eb::PART_ALL) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_ALL, TYC, false, XC>, grid, block, L.smem, P);      \
+      else if (part == eb::PART_FLUID) cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_FLUID, TYC, false, XC>, grid, block, L.smem, P); \
+      else cuda_emu::launch(eb::rhs_fused_kernel<256, 1, GW, AG, eb::PART_TRACERS, TYC, false, XC>, grid, block, L.smem, P);                \
     } while (0)
+#define EMU_PARTS(GW, AG, TYC) EMU_PARTS_X(GW, AG, TYC, false)
     // like launch_part(): the instantiation with the tile shape compiled in where there is one (here
     // 32 x 4 and 32 x 12), else the any-shape one
 #define EMU_LAUNCH(GW, AG)                                                                                            \
     do {                                                                                                              \
-      if (L.tx == 32 && L.ty == 12) EMU_PARTS(GW, AG, 12);                                                            \
+      if (L.xc && L.ty == 12) EMU_PARTS_X(GW, AG, 12, true);                                                          \
+      else if (L.xc && L.ty == 4) EMU_PARTS_X(GW, AG, 4, true);                                                       \
+      else if (L.tx == 32 && L.ty == 12) EMU_PARTS(GW, AG, 12);                                                       \
       else if (L.tx == 32 && L.ty == 4) EMU_PARTS(GW, AG, 4);                                                         \
       else EMU_PARTS(GW, AG, 0);                                                                                      \
     } while (0)
@@ -88,6 +93,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
     else EMU_LAUNCH(false, false);
 #undef EMU_LAUNCH
 #undef EMU_PARTS
+#undef EMU_PARTS_X
   }
   if (P.slow_mode) cuda_emu::launch_plain(eb::slow_post_kernel, dim3(3), dim3(64), P);   // as launch_box() does
   *state_bits = flag;
@@ -119,7 +125,7 @@ extern "C" int emu_face(const eulerb200_config* cfg, const double* const* w, con
   const long nent = eb::face_len(*cfg, f) / (5 + cfg->nchem);
   const dim3 grid((unsigned)((nent + 255) / 256)), block(256);
   if (what == 0) {
-    cuda_emu::launch2(eb::pack_face_kernel, grid, block, g, out, nent);
+    cuda_emu::launch2(eb::pack_face_kernel, dim3((unsigned)((nent + 7) / 8)), dim3(32, 8), g, out, nent);   // as exchange_start() launches it
   } else {
     eb::GhostFace G;
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &G) != 0) return -1;

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport):
+def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport, overlap="1"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -29,6 +29,7 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     os.environ["EULERB200_HALO"] = transport
+    os.environ["EULERB200_OVERLAP"] = overlap
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     pkg = load_package()
@@ -55,25 +56,33 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,nchem,bcs,transport", [
-    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "p2p"),      # periodic in x over 2 ranks: both x-faces go to the same peer
-    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl"),
-    (2, (3, 40, 36), 0, [N] * 6, "p2p"),
-    (4, (24, 28, 20), 2, [P] * 6, "p2p"),
-    (4, (24, 28, 20), 2, [P] * 6, "nccl"),
-    (8, (24, 24, 24), 10, [R] * 6, "p2p"),
-    (8, (3, 64, 48), 0, [N] * 6, "nccl"),
+@pytest.mark.parametrize("world,n,nchem,bcs,transport,overlap", [
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "p2p", "1"),      # periodic in x over 2 ranks: both x-faces go to the same peer
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl", "1"),
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl", "0"),
+    (2, (80, 30, 20), 10, [R] * 6, "nccl", "0"),               # full-width (32-column) tiles next to a rank seam
+    (2, (80, 30, 20), 10, [R] * 6, "p2p", "2"),
+    (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl", "2"),
+    (2, (3, 40, 36), 0, [N] * 6, "p2p", "1"),
+    (4, (24, 28, 20), 2, [P] * 6, "p2p", "0"),
+    (4, (24, 28, 20), 2, [P] * 6, "nccl", "2"),
+    (8, (24, 24, 24), 10, [R] * 6, "p2p", "2"),
+    (8, (24, 24, 24), 10, [R] * 6, "nccl", "0"),
+    (8, (3, 64, 48), 0, [N] * 6, "nccl", "1"),
 ])
-def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem, bcs, transport):
+def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem, bcs, transport, overlap):
     """transport: "p2p" = pack kernels store into the neighbour's ghost slab over NVLink (CUDA IPC)
-    and publish a sequence number; "nccl" = pack + grouped ncclSend/ncclRecv on a side stream."""
+    and publish a sequence number; "nccl" = pack + grouped ncclSend/ncclRecv on a side stream.
+    overlap (EULERB200_OVERLAP): "1" = interior launch behind the exchange, then the boundary shells; "2" = the
+    shells on high-priority streams as soon as the halo is in, next to the interior launch; "0" = exchange first
+    (behind the pre-pass), then one launch over the whole box."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
     import oracle
-    mp.spawn(_worker, args=(world, _free_port(), n, nchem, bcs, str(tmp_path), transport), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, nchem, bcs, str(tmp_path), transport, overlap), nprocs=world, join=True)
     port = oracle.Port()
     w = oracle.random_state(n, nchem, seed=31)
     d = (1.0 / n[0], 1.0 / n[1], 1.0 / n[2])

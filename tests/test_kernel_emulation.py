@@ -205,6 +205,64 @@ def test_emulated_bulk_copy_staging_variant(emu, oracle_mod, port):
         assert max(normwise_errors(got, ref, rounding_floor(w, 1.4, d))) <= 1e-12
 
 
+def test_emulated_full_width_tiles_variant(pkg, emu, oracle_mod, port):
+    """rhs_fused_kernel<..., XC>: tiles own all 32 columns and the x-faces that close a tile on the right come
+    from the idle lanes of the top warp through two mbarriers (column written / column consumed).  Each face is
+    the same arithmetic on the same stencil whoever computes it, so the result must have the bits of the default
+    kernel -- in every synchronisation mode, for tiles cut short by the box in x and in y, boundary tiles of every
+    ghost rule, the AG / GW instantiations, split launches, the slow mode, sub-boxes (interior / shell launches of a
+    decomposed run) -- and the strict build must still be the oracle bit for bit."""
+    from emu.emu import Emu
+    cases = [((70, 23, 5), 10, [P] * 6, 384, {}), ((64, 12, 4), 2, [R, R, P, P, N, N], 384, dict(pair=1)),
+             ((96, 12, 3), 4, [N] * 6, 384, dict(pair=2)), ((33, 11, 3), 3, [R] * 6, 384, dict(pair=2)),
+             ((32, 7, 5), 0, [P, P, N, N, R, R], 128, dict(pair=1)), ((100, 9, 3), 2, [R] * 6, 128, {}),
+             ((65, 14, 3), 2, [N, N, R, R, P, P], 384, dict(aux_in_gen=1, pair=2)),
+             ((67, 13, 3), 4, [P] * 6, 384, dict(split=1, pair=2)), ((45, 12, 3), 1, [R] * 6, 384, dict(use_aux=0))]
+    for n, nchem, bcs, threads, kw in cases:
+        w = oracle_mod.random_state(n, nchem, seed=5 + sum(n))
+        d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+        forcing = [0, 0.25, -0.1, 0, 0.5]
+        ret0, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, **kw)
+        ret1, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, forcing=forcing, threads=threads, xc=1, **kw)
+        assert ret0 == 0 and ret1 == 0
+        assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(base, got)), (n, nchem, kw)
+    # sub-boxes (the interior / shell launches of a decomposed run), against the same launch without XC
+    n, nchem, bcs = (80, 20, 9), 2, [P] * 6
+    w = oracle_mod.random_state(n, nchem, seed=77)
+    d = (0.1, 0.1, 0.1)
+    for lo, hi in [((3, 3, 3), (77, 17, 6)), ((0, 0, 0), (3, 20, 9)), ((3, 0, 0), (77, 3, 9)), ((5, 4, 2), (70, 17, 8))]:
+        pair = 2 if hi[0] - lo[0] >= 31 and hi[1] - lo[1] >= 2 else 0      # (rows of thin boxes are not warps)
+        r0, base, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, pair=pair, lo=lo, hi=hi)
+        r1, got, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, pair=pair, xc=1, lo=lo, hi=hi)
+        assert r0 == 0 and r1 == 0
+        assert not np.isnan(base[0].reshape(n[2], n[1], n[0])[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]]).any()
+        sl = (slice(lo[2], hi[2]), slice(lo[1], hi[1]), slice(lo[0], hi[0]))
+        for a, b in zip(got[:5], base[:5]):
+            assert np.array_equal(a.reshape(n[2], n[1], n[0])[sl], b.reshape(n[2], n[1], n[0])[sl])
+        assert np.array_equal(got[5].reshape(n[2], n[1], n[0], nchem)[sl], base[5].reshape(n[2], n[1], n[0], nchem)[sl])
+    # hook-assigned forcing and the slow mode
+    n, nchem, bcs = (66, 13, 4), 2, [R] * 6
+    w = oracle_mod.random_state(n, nchem, seed=8)
+    rng = np.random.default_rng(10)
+    G = [rng.normal(size=x.size) for x in w]
+    _, g0, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, g_in_wdot=G, pair=2)
+    _, g1, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, g_in_wdot=G, pair=2, xc=1)
+    assert all(np.array_equal(a, b) for a, b in zip(g0, g1))
+    _, s0, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, [x.copy() for x in w], threads=384, energy_units=3.0)
+    _, s1, _ = emu.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, [x.copy() for x in w], threads=384, energy_units=3.0, xc=1)
+    assert all(np.array_equal(a, b) for a, b in zip(s0, s1))
+    # strict build + XC: the oracle's bits
+    emu_s = Emu(pkg, strict=True)
+    for n, nchem, bcs, kw in [((70, 12, 4), 2, [R] * 6, dict(pair=2)), ((64, 13, 3), 0, [P, P, N, N, R, R], {})]:
+        w = oracle_mod.random_state(n, nchem, seed=sum(n))
+        d = (1.0 / n[0], 2.0 / n[1], 0.5 / n[2])
+        ret, got, bits = emu_s.rhs(n, nchem, d, 1.4, bcs, nbr_single(bcs), 0, w, threads=384, xc=1, **kw)
+        ret_ref, ref, _ = port.feuler(port.cfg(n, nchem, d, 1.4, bcs), w)
+        assert ret == 0 and ret_ref == 0 and bits == 0
+        for a, b in zip(got, ref):
+            assert (a is None and b is None) or np.array_equal(a, b), (n, nchem, bcs)
+
+
 def test_emulated_illegal_state_bits(emu, oracle_mod, port):
     n = (10, 8, 6)
     w = oracle_mod.random_state(n, 0, seed=2)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# same-box A/B: default kernel vs the full-width-tile variant (EULERB200_XC=1), parity and sanitizers with it
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+find . -name "*.so" -exec touch {} + ; touch sundials-manyvector-demo_b200/euler3d_b200 2>/dev/null
+find oracle/_ref -type f -exec touch {} + 2>/dev/null
+timeout 300 python tools/tune2.py --n 512 512 512 --nchem 10 --steps 5 --env "" "XC=1" "" "XC=1" "XC=1 PAIR=1" "XC=1 PAIR=0" "XC=1 CTAS=8800" > gpurun_out/x23_tune.log 2>&1
+timeout 100 python tools/tune2.py --n 512 512 512 --nchem 0 --steps 5 --env "" "XC=1" "XC=1 VARIANT=1" > gpurun_out/x23_tune_nchem0.log 2>&1
+EULERB200_XC=1 timeout 200 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/x23_pytest_xc.log 2>&1
+for tool in racecheck synccheck; do
+  EULERB200_XC=1 timeout 400 compute-sanitizer --tool $tool --target-processes all --print-limit 20 \
+     python -m pytest tests/test_gpu_parity.py -x -q -k "test_feuler_matches_oracle" > gpurun_out/x23_sanitize_${tool}_xc.log 2>&1
+  echo "rc=$?" >> gpurun_out/x23_sanitize_${tool}_xc.log
+done
+echo done > gpurun_out/x23_done.txt
