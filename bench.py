@@ -544,8 +544,10 @@ def main():
             allp = [mine]
         if rank == 0:
             timeline = {"unit": "ms per RHS, device time (eulerb200_profile)", "per_rank": allp,
-                        "note": "transfer runs on a side stream concurrently with interior; rhs = whole call on the "
-                                "launching stream"}
+                        "note": "transfer = halo pack + send/receive on the exchange stream (highest priority), "
+                                "concurrent with prepass and interior; pack = what of it the launching stream waits for; "
+                                "shells = what is left of the boundary shells after the interior launch "
+                                "(EULERB200_OVERLAP=2: they run beside it); rhs = whole call on the launching stream"}
     except Exception as ex:      # pragma: no cover
         timeline = {"error": str(ex)[:200]}
 

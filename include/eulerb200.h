@@ -140,7 +140,10 @@ int eulerb200_rhs_host(eulerb200_ctx* ctx, double t, const double* const* w_host
 int eulerb200_rhs_any(eulerb200_ctx* ctx, double t, const double* const* w, double* const* wdot,
                       void* stream);
 
-/* EulerData::ExchangeStart / ExchangeEnd (euler3D.hpp:577-1191), callable on their own. */
+/* EulerData::ExchangeStart / ExchangeEnd (euler3D.hpp:577-1191), callable on their own.
+ * The packing runs on the library's exchange stream behind the work queued on `stream` so far:
+ * w must stay unchanged until exchange_end has been queued on the stream that next writes it
+ * (the reference packs inside ExchangeStart; fEuler, the only caller, never writes w). */
 int eulerb200_exchange_start(eulerb200_ctx* ctx, const double* const* w, void* stream);
 int eulerb200_exchange_end(eulerb200_ctx* ctx, void* stream);
 /* Ghost layers of one face in the reference's receive-buffer layout (Wrecv..Frecv,

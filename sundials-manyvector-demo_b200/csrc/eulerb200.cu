@@ -418,7 +418,7 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
       if (!c->remote[f]) continue;
       const long nent = eb::face_len(c->cfg, f) / nv;
       double* dst = reinterpret_cast<double*>(c->peer_base[f] + c->peer_slab_off[f][par]);
-      eb::pack_face_kernel<<<(unsigned)((nent + 7) / 8), dim3(32, 8), 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
+      eb::pack_face_warp_kernel<<<(unsigned)((nent + 7) / 8), dim3(32, 8), 0, c->comm_stream>>>(face_geom(c, f, w), dst, nent);
       halo_signal_kernel<<<1, 1, 0, c->comm_stream>>>(
           reinterpret_cast<unsigned long long*>(c->peer_base[f] + c->peer_arrival_off[f]), c->seq);
       c->launches += 2;
@@ -431,16 +431,18 @@ int exchange_start(eulerb200_ctx* c, const double* const* w, cudaStream_t s)
     return 0;
   }
   if (!c->comm) return fail(c, -3, "context has remote neighbours but neither eulerb200_comm_attach nor eulerb200_p2p_attach was called");
-  for (int f = 0; f < 6; f++) {
-    if (!c->remote[f]) continue;
-    const long nent = eb::face_len(c->cfg, f) / nv;
-    eb::pack_face_kernel<<<(unsigned)((nent + 7) / 8), dim3(32, 8), 0, s>>>(face_geom(c, f, w), c->send[f], nent);
-    c->launches++;
-  }
-  EB_CUDA(c, cudaGetLastError());
+  // pack on the exchange stream as well: it only needs w as it is when this call is made (everything queued
+  // on s so far), so nothing the caller launches on s afterwards -- the pre-pass, the interior -- waits for it
   EB_CUDA(c, cudaEventRecord(c->ev_packed, s));
   EB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_packed, 0));
   EB_PREC(c, 6, c->comm_stream);
+  for (int f = 0; f < 6; f++) {
+    if (!c->remote[f]) continue;
+    const long nent = eb::face_len(c->cfg, f) / nv;
+    eb::pack_face_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->comm_stream>>>(face_geom(c, f, w), c->send[f], nent);
+    c->launches++;
+  }
+  EB_CUDA(c, cudaGetLastError());
   eb::ExchangeOp ops[12];
   const int nops = eb::exchange_plan(c->cfg, ops);
   EB_NCCL(c, nccl().GroupStart());
@@ -882,6 +884,10 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
   }
   c->prof_pack_first = false;
   EB_PREC(c, 0, s);
+  // the exchange is started before the pre-pass is queued, so that its pack kernels (on the exchange stream)
+  // do not wait for it (slow mode: the pre-pass rebuilds the total energy the pack reads, so it goes first)
+  const bool early_start = c->any_remote && !slow_mode;
+  if (early_start && (rc = exchange_start(c, w, s))) return rc;
   {
     int rc_ = launch_aux(c, P, 0, P.nz, s);
     if (rc_) return rc_;
@@ -897,8 +903,7 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
   // Overlap (the structure of utilities.cpp:61 -> 76-116 -> 119 -> 123-195): start the
   // exchange, evaluate every cell whose stencils stay clear of the remote faces, wait for
   // the halos, then evaluate the remaining shell as non-overlapping slabs.
-  rc = exchange_start(c, w, s);
-  if (rc) return rc;
+  if (!early_start && (rc = exchange_start(c, w, s))) return rc;
   for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
   EB_PREC(c, 2, s);
   const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low

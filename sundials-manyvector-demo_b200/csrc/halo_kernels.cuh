@@ -1,6 +1,7 @@
 // ---------------------------------------------------------------------------
 // halo_kernels.cuh -- the two face kernels of the halo exchange (sm_100a; O(surface), HBM bound):
-//   pack_face_kernel   ExchangeStart's send-buffer packing (euler3D.hpp:644-786); the destination
+//   pack_face_kernel / pack_face_warp_kernel
+//                      ExchangeStart's send-buffer packing (euler3D.hpp:644-786); the destination
 //                      is the local send slab (NCCL transport) or the neighbour's ghost slab
 //                      (peer-store transport)
 //   ghost_face_kernel  a face's ghost layers in the reference's receive-buffer layout, whatever
@@ -41,11 +42,29 @@ EB_HD long face_cell(const FaceGeom& g, long src, long a, long b)
 // What this rank sends through face f: its three layers nearest that face in increasing
 // index order, all NVAR values of a cell contiguous (euler3D.hpp:644-786).
 #if defined(__CUDACC__) || defined(EB_CUDA_EMU)
-// Launch with blocks of 32 x 8 threads: a warp (threadIdx.y) packs one entry, its lanes the NVAR values
-// of that cell, so that every store instruction writes one contiguous run of the destination -- which
-// matters when the destination is the neighbour's slab across NVLink (peer-store transport: a
-// thread-per-entry kernel issues NVAR scattered 8-byte remote stores per thread; measured 38 GB/s).
+// One thread per entry (cell of a layer): the reads of neighbouring threads are neighbouring cells.  For a
+// local destination (the send slab of the NCCL transport): 0.11 ms per 512^2 face.
 __global__ void pack_face_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
+{
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < nent; e += (long)gridDim.x * blockDim.x) {
+  int d; long a, b, na;
+  face_decode(g, e, d, a, b, na);
+  const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);
+  const long src = (g.f % 2 == 0) ? d : n - 3 + d;
+  const long cell = face_cell(g, src, a, b);
+  const int nv = 5 + g.nchem;
+  double* o = buf + (long)nv * e;
+#pragma unroll
+  for (int v = 0; v < 5; v++) o[v] = g.w[v][cell];
+  for (int v = 0; v < g.nchem; v++) o[5 + v] = g.w[5][cell * g.nchem + v];
+  }
+}
+
+// The same with one WARP per entry (blocks of 32 x 8 threads; threadIdx.y picks the entry, the lanes its NVAR
+// values), so that every store instruction writes one contiguous run of the destination -- for a destination
+// across NVLink (the neighbour's ghost slab, peer-store transport), where the thread-per-entry kernel's
+// NVAR scattered 8-byte remote stores per thread reach 38 GB/s (2.5 ms per face; this one 0.6 ms).
+__global__ void pack_face_warp_kernel(const FaceGeom g, double* __restrict__ buf, long nent)
 {
   const int nv = 5 + g.nchem;
   const long n = (g.f / 2 == 0) ? g.nx : (g.f / 2 == 1 ? g.ny : g.nz);

@@ -61,7 +61,7 @@ class Emu:
         out = np.full((5 + nchem) * 3 * other, np.nan)
         self.lib.emu_face.restype = C.c_int
         ret = self.lib.emu_face(C.byref(c), _ptrs(w), _ptrs(recv) if recv is not None else None, f,
-                                0 if what == "pack" else 1, out.ctypes.data_as(_dp))
+                                {"pack": 0, "ghost": 1, "pack_warp": 2}[what], out.ctypes.data_as(_dp))
         assert ret == 0
         return out
 

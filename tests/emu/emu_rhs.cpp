@@ -125,7 +125,9 @@ extern "C" int emu_face(const eulerb200_config* cfg, const double* const* w, con
   const long nent = eb::face_len(*cfg, f) / (5 + cfg->nchem);
   const dim3 grid((unsigned)((nent + 255) / 256)), block(256);
   if (what == 0) {
-    cuda_emu::launch2(eb::pack_face_kernel, dim3((unsigned)((nent + 7) / 8)), dim3(32, 8), g, out, nent);   // as exchange_start() launches it
+    cuda_emu::launch2(eb::pack_face_kernel, grid, block, g, out, nent);
+  } else if (what == 2) {        // the peer-store transport's pack, as exchange_start() launches it
+    cuda_emu::launch2(eb::pack_face_warp_kernel, dim3((unsigned)((nent + 7) / 8)), dim3(32, 8), g, out, nent);
   } else {
     eb::GhostFace G;
     if (eb::ghost_face(*cfg, f, recv ? recv[f] : nullptr, &G) != 0) return -1;

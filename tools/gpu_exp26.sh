@@ -7,7 +7,7 @@ find . -name "*.so" -exec touch {} + ; touch sundials-manyvector-demo_b200/euler
 find oracle/_ref -type f -exec touch {} + 2>/dev/null
 N=${NGPU:-2}
 port=29520
-for ov in ${OVS:-1 0}; do for halo in nccl p2p; do
+for ov in ${OVS:-1 0}; do for halo in ${HALOS:-nccl p2p}; do
   port=$((port+1))
   EULERB200_OVERLAP=$ov EULERB200_HALO=$halo timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
      bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/x${TAG:-26}_bench_n${N}_ov${ov}_${halo}.json 2> gpurun_out/x${TAG:-26}_bench_n${N}_ov${ov}_${halo}.err
