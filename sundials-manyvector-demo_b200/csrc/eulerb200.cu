@@ -175,6 +175,8 @@ struct eulerb200_ctx {
   int overlap = 1;               // EULERB200_OVERLAP: 1 interior launch behind the halo exchange, then the shell launches;
                                  // 2 shells on high-priority streams as soon as the halo is in; 0 exchange first, one launch (rhs_impl)
   bool prof_pack_first = false;
+  int thick_shells = 0;          // EULERB200_SHELLS=1: boundary shells one tile thick in x and y (default: three layers;
+                                 // measured no faster: 60.42 vs 60.20 ms at 2 GPUs, the cost is in the boundary tiles themselves)
   int xc = 1;                    // EULERB200_XC=0: 31-column tiles (default: tiles own all 32 columns, the closing x-faces come
                                  // from the top warp; 59.2 vs 61.1 ms at 512^3 / NVAR 15)
   int variant_part[3] = {0, 0, 0};   // compiled variant per part (ALL, FLUID, TRACERS)
@@ -561,6 +563,7 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
   if (const char* ev = getenv("EULERB200_SPLIT")) c->split = atoi(ev) != 0;
   if (const char* ev = getenv("EULERB200_STAGE")) c->stage = atoi(ev) != 0;
   if (const char* ev = getenv("EULERB200_XC")) c->xc = atoi(ev) != 0;
+  if (const char* ev = getenv("EULERB200_SHELLS")) c->thick_shells = atoi(ev) != 0;
   if (const char* ev = getenv("EULERB200_OVERLAP")) c->overlap = std::max(0, std::min(2, atoi(ev)));
   for (int x_ = 0; x_ < 2; x_++) for (int a_ = 0; a_ < 6; a_++) for (int b_ = 0; b_ < 3; b_++) for (int d_ = 0; d_ < 3; d_++) c->carveout_for[x_][a_][b_][d_] = (size_t)-1;
   if (cfg->device >= 0) {
@@ -850,12 +853,20 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     P.et_rw = const_cast<double*>(w[4]);
   }
   const long n[3] = {P.nx, P.ny, P.nz};
-  long lo[3], hi[3];
-  bool interior = true;
-  for (int d = 0; d < 3; d++) {
-    lo[d] = c->remote[2 * d] ? 3 : 0;
-    hi[d] = n[d] - (c->remote[2 * d + 1] ? 3 : 0);
-    if (hi[d] <= lo[d]) interior = false;
+  // interior box and boundary shells (host_setup.h: overlap_boxes), cut along the tile grid of a launch over
+  // the whole box
+  eb::BoxList B;
+  B.count = 0;
+  bool interior = false;
+  if (c->any_remote) {
+    const long z0[3] = {0, 0, 0};
+    const int vi0 = c->variant_part[0];
+    const eb::LaunchGeom L0 = eb::launch_geom(z0, n, 5 + P.nchem, kVariants[vi0].threads, c->pair_sync, c->ctas_target,
+                                              c->xc && kVariants[vi0].fnx[0][0] != nullptr);
+    const long pitch[3] = {L0.xc ? L0.tx : L0.tx - 1, L0.ty - 1, L0.seg_len};
+    bool rem[6];
+    for (int f = 0; f < 6; f++) rem[f] = c->remote[f];
+    interior = eb::overlap_boxes(n, rem, pitch, c->thick_shells != 0 && L0.tx == 32 && L0.ty == kVariants[vi0].threads / 32, &B);
   }
   int rc;
   if (c->any_remote && (!c->overlap || !interior)) {
@@ -906,13 +917,8 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
   if (!early_start && (rc = exchange_start(c, w, s))) return rc;
   for (int f = 0; f < 6; f++) eb::ghost_face(c->cfg, f, c->recv_cur[f], &P.ghost[f]);   // slabs of this exchange
   EB_PREC(c, 2, s);
-  const long a0[3] = {0, 0, 0}, a1[3] = {n[0], n[1], lo[2]};                   // z-low
-  const long b0[3] = {0, 0, hi[2]}, b1[3] = {n[0], n[1], n[2]};                 // z-high
-  const long c0[3] = {0, 0, lo[2]}, c1[3] = {n[0], lo[1], hi[2]};               // y-low
-  const long d0[3] = {0, hi[1], lo[2]}, d1[3] = {n[0], n[1], hi[2]};            // y-high
-  const long e0[3] = {0, lo[1], lo[2]}, e1[3] = {lo[0], hi[1], hi[2]};          // x-low
-  const long f0[3] = {hi[0], lo[1], lo[2]}, f1[3] = {n[0], hi[1], hi[2]};       // x-high
-  const long* box[6][2] = {{a0, a1}, {b0, b1}, {c0, c1}, {d0, d1}, {e0, e1}, {f0, f1}};
+  const long* lo = B.lo[0];
+  const long* hi = B.hi[0];
   if (c->overlap == 2) {
     // Early shells: the slabs do not depend on the interior launch, only on the pre-pass (per-cell arrays)
     // and on the halo.  They go to three high-priority streams that wait for exactly those two, so their
@@ -928,14 +934,8 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     if (rc) return rc;
     EB_CUDA(c, cudaEventRecord(c->ev_halo, c->slab_stream[0]));
     for (int h = 1; h < 3; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_halo, 0));
-    int q = 0;
-    for (int b = 0; b < 6; b++) {
-      bool empty = false;
-      for (int d = 0; d < 3; d++) if (box[b][1][d] <= box[b][0][d]) empty = true;
-      if (empty) continue;
-      if ((rc = launch_box(c, P, box[b][0], box[b][1], c->slab_stream[q % 3]))) return rc;
-      q++;
-    }
+    for (int b = 1; b < B.count; b++)
+      if ((rc = launch_box(c, P, B.lo[b], B.hi[b], c->slab_stream[(b - 1) % 3]))) return rc;
     for (int h = 0; h < 3; h++) {
       EB_CUDA(c, cudaEventRecord(c->ev_join[h], c->slab_stream[h]));
       EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[h], 0));
@@ -955,14 +955,8 @@ static int rhs_impl(eulerb200_ctx* c, const double* const* w, double* const* wdo
     cudaStream_t lane[3] = {s, c->slab_stream[0], c->slab_stream[1]};
     EB_CUDA(c, cudaEventRecord(c->ev_fork, s));
     for (int h = 0; h < 2; h++) EB_CUDA(c, cudaStreamWaitEvent(c->slab_stream[h], c->ev_fork, 0));
-    int q = 0;
-    for (int b = 0; b < 6; b++) {
-      bool empty = false;
-      for (int d = 0; d < 3; d++) if (box[b][1][d] <= box[b][0][d]) empty = true;
-      if (empty) continue;
-      if ((rc = launch_box(c, P, box[b][0], box[b][1], lane[q % 3]))) return rc;
-      q++;
-    }
+    for (int b = 1; b < B.count; b++)
+      if ((rc = launch_box(c, P, B.lo[b], B.hi[b], lane[(b - 1) % 3]))) return rc;
     for (int h = 0; h < 2; h++) {
       EB_CUDA(c, cudaEventRecord(c->ev_join[h], c->slab_stream[h]));
       EB_CUDA(c, cudaStreamWaitEvent(s, c->ev_join[h], 0));

@@ -215,4 +215,45 @@ inline double boundary_tile_fraction(const long lo[3], const long hi[3], long nx
   return 1.0 - ((double)okx / L.gx) * ((double)oky / L.gy);
 }
 
+// The launches of one RHS of a rank with remote neighbours (rhs_impl): box 0 is the interior -- every cell
+// whose stencils stay clear of the remote faces, evaluated while the halo is on its way -- boxes 1.. are
+// the boundary shells (z-low, z-high, y-low, y-high, x-low, x-high; empty ones left out), evaluated once
+// it is in.  Together they cover the box exactly once.
+// A shell holds the three layers next to its face.  thick (EULERB200_SHELLS=1): in x and y it is one TILE thick
+// instead (pitch[d] = columns / rows a tile owns) and cut where the tile grid of the whole box has a seam, so
+// that interior and shell launches together run the tiles a single launch over the box would run -- full
+// tiles, no 3-of-4-column CTAs; thin boxes (fewer than four tiles along an axis) keep three layers, and along z a
+// shell is always three planes (z-segments are not a tiling).  Measured at 512^3 / NVAR 15 on 2 GPUs: the
+// 32-column shell takes 4.9 ms after a 53.7 ms interior, 60.42 ms in all against 60.20 with the 3-column shell
+// (57.4 + 0.93): the 2.5 x per-cell cost of a shell is in its boundary tiles (halo reads, short z-segments),
+// not in the thin tiles -- so three layers stay the default.
+struct BoxList { int count; long lo[7][3], hi[7][3]; };
+inline bool overlap_boxes(const long n[3], const bool remote[6], const long pitch[3], bool thick, BoxList* B)
+{
+  long lo[3], hi[3];
+  bool interior = true;
+  for (int d = 0; d < 3; d++) {
+    const bool tile = thick && d < 2 && pitch[d] >= 3 && n[d] >= 4 * pitch[d];
+    lo[d] = remote[2 * d] ? (tile ? pitch[d] : 3) : 0;
+    hi[d] = n[d];
+    if (remote[2 * d + 1]) hi[d] = tile ? lo[d] + pitch[d] * ((n[d] - 3 - lo[d]) / pitch[d]) : n[d] - 3;
+    if (hi[d] <= lo[d]) interior = false;
+  }
+  B->count = 0;
+  if (!interior) return false;
+  auto add = [&](long x0, long x1, long y0, long y1, long z0, long z1) {
+    if (x1 <= x0 || y1 <= y0 || z1 <= z0) return;
+    const int q = B->count++;
+    B->lo[q][0] = x0; B->hi[q][0] = x1; B->lo[q][1] = y0; B->hi[q][1] = y1; B->lo[q][2] = z0; B->hi[q][2] = z1;
+  };
+  add(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);        // interior
+  add(0, n[0], 0, n[1], 0, lo[2]);                      // z-low
+  add(0, n[0], 0, n[1], hi[2], n[2]);                   // z-high
+  add(0, n[0], 0, lo[1], lo[2], hi[2]);                 // y-low
+  add(0, n[0], hi[1], n[1], lo[2], hi[2]);              // y-high
+  add(0, lo[0], lo[1], hi[1], lo[2], hi[2]);            // x-low
+  add(hi[0], n[0], lo[1], hi[1], lo[2], hi[2]);         // x-high
+  return true;
+}
+
 }  // namespace eb

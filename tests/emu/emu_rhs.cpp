@@ -106,6 +106,23 @@ extern "C" int emu_decompose(int nprocs, int rank, const int64_t* n, const int32
   return eb::decompose(nprocs, rank, n, bc, dims, coords, ext, nbr);
 }
 
+// The interior / shell boxes rhs_impl() launches for a rank with the given remote faces (host_setup.h), with the
+// tile pitches of the launch geometry of the whole box.  out: count, then lo[3], hi[3] per box.
+extern "C" int emu_overlap_boxes(const long* n, const int* remote, int nchem, int threads, int xc, int thick, long* out)
+{
+  const long z[3] = {0, 0, 0};
+  const eb::LaunchGeom L = eb::launch_geom(z, n, 5 + nchem, threads, 2, 5920, xc);
+  const long pitch[3] = {L.xc ? L.tx : L.tx - 1, L.ty - 1, L.seg_len};
+  bool rem[6];
+  for (int f = 0; f < 6; f++) rem[f] = remote[f] != 0;
+  eb::BoxList B;
+  const bool ok = eb::overlap_boxes(n, rem, pitch, thick != 0, &B);
+  out[0] = ok ? B.count : 0;
+  for (int q = 0; q < B.count; q++)
+    for (int d = 0; d < 3; d++) { out[1 + 6 * q + d] = B.lo[q][d]; out[1 + 6 * q + 3 + d] = B.hi[q][d]; }
+  return ok ? 0 : 1;
+}
+
 extern "C" double emu_boundary_tile_fraction(const long* lo, const long* hi, long nx, long ny, int nchem, int threads)
 {
   const eb::LaunchGeom L = eb::launch_geom(lo, hi, 5 + nchem, threads, 2);

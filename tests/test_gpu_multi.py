@@ -29,7 +29,8 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport, overlap="1")
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     os.environ["EULERB200_HALO"] = transport
-    os.environ["EULERB200_OVERLAP"] = overlap
+    os.environ["EULERB200_OVERLAP"] = overlap[0]
+    os.environ["EULERB200_SHELLS"] = "1" if overlap.endswith("t") else "0"      # "1t": tile-thick boundary shells
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     pkg = load_package()
@@ -63,6 +64,10 @@ def _worker(rank, world, port_no, n, nchem, bcs, outdir, transport, overlap="1")
     (2, (80, 30, 20), 10, [R] * 6, "nccl", "0"),               # full-width (32-column) tiles next to a rank seam
     (2, (80, 30, 20), 10, [R] * 6, "p2p", "2"),
     (2, (40, 24, 20), 2, [P, P, R, R, N, N], "nccl", "2"),
+    (2, (272, 50, 12), 2, [R] * 6, "nccl", "1t"),              # 136 columns per rank: tile-thick x-shell (32 columns)
+    (2, (272, 50, 12), 2, [P, P, R, R, N, N], "p2p", "2t"),    # ... on both sides (periodic over 2 ranks)
+    (2, (272, 50, 12), 2, [P, P, R, R, N, N], "nccl", "1"),
+    (4, (272, 100, 8), 2, [P] * 6, "nccl", "2t"),              # tile-thick shells in x and y
     (2, (3, 40, 36), 0, [N] * 6, "p2p", "1"),
     (4, (24, 28, 20), 2, [P] * 6, "p2p", "0"),
     (4, (24, 28, 20), 2, [P] * 6, "nccl", "2"),
@@ -75,7 +80,8 @@ def test_decomposed_cuda_rhs_equals_single_rank_oracle(tmp_path, world, n, nchem
     and publish a sequence number; "nccl" = pack + grouped ncclSend/ncclRecv on a side stream.
     overlap (EULERB200_OVERLAP): "1" = interior launch behind the exchange, then the boundary shells; "2" = the
     shells on high-priority streams as soon as the halo is in, next to the interior launch; "0" = exchange first
-    (behind the pre-pass), then one launch over the whole box."""
+    (behind the pre-pass), then one launch over the whole box; a trailing "t" = tile-thick boundary shells
+    (EULERB200_SHELLS=1)."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)

@@ -154,3 +154,52 @@ def test_native_driver_help_and_option_errors_need_no_gpu(pkg):
                       (["--order=0", "--etable=12"], "needs fixedstep = 1")):
         out = subprocess.run([exe] + args, capture_output=True, text=True)
         assert out.returncode == 1 and msg in out.stderr, (args, out.stderr)
+
+
+def test_interior_and_shell_boxes_cover_the_box_once_and_follow_the_tile_grid():
+    """eb::overlap_boxes (host_setup.h), the launches rhs_impl() makes for a rank with remote neighbours: the
+    interior box keeps three cells from every remote face, interior + shells cover the box exactly once, and with
+    tile-thick shells (default) every cut in x and y lies on a seam of the tile grid a single launch over the box
+    would use (32 owned columns / 11 owned rows at 384 threads), so no launch runs 3-of-4-column tiles."""
+    from emu.emu import build
+    lib = C.CDLL(build())
+    L3, I6 = C.c_long * 3, C.c_int * 6
+    out = (C.c_long * 64)()
+
+    def boxes(n, remote, nchem=10, xc=1, thick=1):
+        rc = lib.emu_overlap_boxes(L3(*n), I6(*remote), nchem, 384, xc, thick, out)
+        cnt = out[0]
+        return rc, [(tuple(out[1 + 6 * q + d] for d in range(3)), tuple(out[4 + 6 * q + d] for d in range(3))) for q in range(cnt)]
+
+    for n, remote, thick in [((512, 512, 512), (0, 1, 0, 1, 0, 1), 1), ((512, 512, 512), (1, 0, 1, 0, 1, 0), 1),
+                             ((512, 512, 512), (1, 1, 1, 1, 1, 1), 1), ((200, 90, 40), (1, 1, 0, 1, 1, 0), 1),
+                             ((512, 512, 512), (1, 1, 1, 1, 1, 1), 0), ((40, 24, 20), (1, 1, 0, 0, 0, 0), 1),
+                             ((3, 4096, 2048), (0, 0, 1, 1, 1, 1), 1)]:
+        rc, bl = boxes(n, remote, thick=thick)
+        assert rc == 0 and len(bl) == 1 + sum(remote)
+        cover = np.zeros((n[2] // 1, n[1], n[0]), dtype=np.int8) if n[0] * n[1] * n[2] <= 1 << 24 else None
+        vol = 0
+        for lo, hi in bl:
+            assert all(0 <= lo[d] < hi[d] <= n[d] for d in range(3))
+            vol += (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2])
+            if cover is not None:
+                cover[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]] += 1
+        assert vol == n[0] * n[1] * n[2]
+        if cover is not None:
+            assert (cover == 1).all()
+        else:          # disjoint by construction of the six slabs around box 0: check pairwise
+            for a in range(len(bl)):
+                for b in range(a + 1, len(bl)):
+                    assert any(bl[a][1][d] <= bl[b][0][d] or bl[b][1][d] <= bl[a][0][d] for d in range(3))
+        lo, hi = bl[0]
+        for d in range(3):
+            assert lo[d] >= (3 if remote[2 * d] else 0) and hi[d] <= n[d] - (3 if remote[2 * d + 1] else 0)
+    # 512^3, all faces remote, 384 threads with full-width tiles: cuts at multiples of 32 (x) and 11 (y), 3 planes in z
+    rc, bl = boxes((512, 512, 512), (1, 1, 1, 1, 1, 1))
+    assert bl[0] == ((32, 11, 3), (480, 506, 509))
+    rc, bl = boxes((512, 512, 512), (0, 1, 0, 1, 0, 1))
+    assert bl[0] == ((0, 0, 0), (480, 506, 509))
+    rc, bl = boxes((512, 512, 512), (1, 1, 1, 1, 1, 1), thick=0)
+    assert bl[0] == ((3, 3, 3), (509, 509, 509))
+    rc, bl = boxes((512, 512, 512), (1, 0, 0, 0, 0, 0), xc=0)        # 31-column tiles
+    assert bl[0] == ((31, 0, 0), (512, 512, 512))

@@ -13,6 +13,6 @@ for ov in ${OVS:-1 0}; do for halo in ${HALOS:-nccl p2p}; do
      bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/x${TAG:-26}_bench_n${N}_ov${ov}_${halo}.json 2> gpurun_out/x${TAG:-26}_bench_n${N}_ov${ov}_${halo}.err
 done; done
 if [ "$N" = "2" ] && [ -z "$SKIP_PYTEST" ]; then
-  timeout 600 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/x${TAG:-26}_pytest_multi_n$N.log 2>&1
+  timeout 600 python -m pytest tests/test_gpu_multi.py -x -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/x${TAG:-26}_pytest_multi_n$N.log 2>&1
 fi
 echo done > gpurun_out/x${TAG:-26}_done_n$N.txt
