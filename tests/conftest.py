@@ -54,6 +54,7 @@ def native_emu_exe(tmp_path_factory):
 
 
 EPS = 2.220446049250313e-16
+FLOOR_CAP = 1e-13      # largest share of a sub-vector's scale that rounding_floor() may forgive (see normwise_errors)
 
 
 def rounding_floor(parts, gamma, d, ulps=32.0):
@@ -95,7 +96,7 @@ def self_noise(port, port_fma, cfg, parts):
 
 def normwise_errors(got, ref, floor=None):
     """The parity metric (DESIGN.md "Tolerance"): per sub-vector
-        max(0, max|got-ref| - floor_f) / scale_f ,   required <= 1e-12,
+        max(0, max|got-ref| - min(floor_f, 1e-13 scale_f)) / scale_f ,   required <= 1e-12,
     scale_f = max|ref_f| (the three momentum components share the scale of the momentum VECTOR:
     a component whose exact right-hand side is zero, e.g. mx in Rayleigh-Taylor, holds only
     rounding residue in the reference too), floor_f = rounding_floor() or 0."""
@@ -109,7 +110,10 @@ def normwise_errors(got, ref, floor=None):
         scale = mom if f in (1, 2, 3) else float(np.abs(b).max())
         err = float(np.abs(a - b).max())
         if floor is not None:
-            err = max(0.0, err - floor[k])
+            # the floor never moves the bar by more than a tenth of it: at most 1e-13 of the scale is forgiven
+            # (where the state is so smooth that rounding of the flux terms exceeds that, a test has to use the
+            # reference's own self-noise as its bar, as the blast-state tests do -- not a bigger floor)
+            err = max(0.0, err - min(floor[k], FLOOR_CAP * scale))
         out.append(err / scale if scale > 0 else err)
         k += 1
     return out
