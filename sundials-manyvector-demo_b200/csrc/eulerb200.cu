@@ -265,7 +265,7 @@ eb::RhsParams make_params(eulerb200_ctx* c, const double* const* w, double* cons
   P.nx = g.nxl; P.ny = g.nyl; P.nz = g.nzl;
   P.nchem = g.nchem;
   P.gamma = g.gamma;
-  P.rdx = 1.0 / g.dx; P.rdy = 1.0 / g.dy; P.rdz = 1.0 / g.dz;
+  P.rdx = EB_RD_SCALE / g.dx; P.rdy = EB_RD_SCALE / g.dy; P.rdz = EB_RD_SCALE / g.dz;
   P.dx = g.dx; P.dy = g.dy; P.dz = g.dz;
   for (int f = 0; f < 5; f++) P.forcing[f] = g.forcing[f];
   for (int f = 0; f < 6; f++) {

@@ -64,7 +64,7 @@ struct RhsParams {
   int nchem;
   int seg_len;              // cells per z-segment
   double gamma;
-  double rdx, rdy, rdz;     // 1/dx, 1/dy, 1/dz
+  double rdx, rdy, rdz;     // EB_RD_SCALE / dx, dy, dz: the inverse spacings, halved where the faces hand out twice the flux (EB_FOLD_HALF)
   double dx, dy, dz;        // (the strict build divides as the reference does, utilities.cpp:202-207)
   double forcing[5];        // constant forcing assigned into wdot (external_forces hook)
   const double* w[6];       // rho, mx, my, mz, et (SoA), chem (AoS, species fastest)
@@ -473,8 +473,28 @@ struct EmitDiv {
            + (zup - zl[q * TR()]) * P.rdz;
 #endif
   }
+#if !defined(EB_STRICT) && !defined(EB_TRUE_DIVISION)
+  // minus the divergence, formed with the differences the other way round: bit for bit 0 - close_next() but
+  // for the sign of a zero, without the subtraction from zero
+  EB_HD double close_next_neg(int q, double zup) const
+  {
+    return ((fx[q * TRX()] - (XU ? fxu[q * TRX()] : fx[q * TRX() + 1])) * P.rdx + (fy[q * T()] - fy[q * T() + TX]) * P.rdy)
+           + (zl[q * TR()] - zup) * P.rdz;
+  }
+#endif
   EB_HD void pair_next(double za, double zb, bool two)    // two == false: the odd species out, zb unused
   {
+#if !defined(EB_STRICT) && !defined(EB_TRUE_DIVISION)
+    if (fast) {                         // (nchem even: always two)
+      const double na = close_next_neg(0, za), nb = close_next_neg(1, zb);
+      zl[0] = za;
+      zl[TR()] = zb;
+      st_out2(dst, na, nb);
+      fx += 2 * TRX(); fy += 2 * T(); zl += 2 * TR(); dst += 2;
+      if (XU) fxu += 2 * TRX();
+      return;
+    }
+#endif
     const double da = close_next(0, za);
     zl[0] = za;
     if (fast) {                         // (nchem even: always two)

@@ -17,7 +17,7 @@ extern "C" int emu_rhs(const eulerb200_config* cfg, const double* const* w, doub
   P.nx = cfg->nxl; P.ny = cfg->nyl; P.nz = cfg->nzl;
   P.nchem = cfg->nchem;
   P.gamma = cfg->gamma;
-  P.rdx = 1.0 / cfg->dx; P.rdy = 1.0 / cfg->dy; P.rdz = 1.0 / cfg->dz;
+  P.rdx = EB_RD_SCALE / cfg->dx; P.rdy = EB_RD_SCALE / cfg->dy; P.rdz = EB_RD_SCALE / cfg->dz;
   P.dx = cfg->dx; P.dy = cfg->dy; P.dz = cfg->dz;
   for (int f = 0; f < 5; f++) P.forcing[f] = cfg->forcing[f];
   for (int f = 0; f < 6; f++) { P.w[f] = w[f]; P.wdot[f] = wdot[f]; }

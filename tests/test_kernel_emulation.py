@@ -51,6 +51,30 @@ def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, th
     assert ret == 0 and max(normwise_errors(got3, ref, floor)) <= 1e-12
 
 
+def _golden_ids():
+    import os
+    from test_oracle import FEULER_FILES
+    return FEULER_FILES, [os.path.basename(p)[7:-4] for p in FEULER_FILES]
+
+
+@pytest.mark.parametrize("path", _golden_ids()[0], ids=_golden_ids()[1])
+def test_emulated_kernel_vs_reference_golden(emu, path):
+    """The reference's golden fEuler cases through the emulated kernel with the bar of the GPU test
+    (tests/test_gpu_golden_and_halo.py::test_cuda_feuler_vs_reference_golden), so that an arithmetic change that
+    costs parity margin shows on the CPU tier first.  The emulation rounds as the GPU does except where nvcc
+    contracts a product and a sum that g++ -ffp-contract=off leaves apart; the smooth advection case, whose
+    right-hand side is rounding noise of the flux terms (the reference's own FMA self-noise there is 0.74e-12
+    in e_t), came out at 1.19e-12 on both tiers with the shared-projection variant of fluid_face and stays at
+    0.91e-12 with the default."""
+    from test_oracle import load_case
+    c = load_case(path)
+    n = tuple(c["n"])
+    ret, got, bits = emu.rhs(n, c["nchem"], c["d"], c["gamma"], c["bcs"], nbr_single(c["bcs"]), 0, c["w"],
+                             forcing=list(c["forcing"]), threads=128)
+    assert ret == 0 and bits == 0
+    assert max(normwise_errors(got, c["wdot"], rounding_floor(c["w"], c["gamma"], c["d"]))) <= 1e-12
+
+
 @pytest.mark.parametrize("bcs", [[D] * 6, [R, R, D, D, N, N], [D, D, P, P, R, R]])
 def test_emulated_boundary_instantiation_with_dirichlet_ghosts(emu, oracle_mod, port, bcs):
     """AG instantiation: Dirichlet ghosts negate rho and e_t, so their 1/rho, p, c cannot come from

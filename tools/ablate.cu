@@ -62,7 +62,7 @@ int main(int argc, char** argv)
   cfg.nxl = cfg.nyl = cfg.nzl = n; cfg.nchem = nchem; cfg.dx = cfg.dy = cfg.dz = 1.0 / n; cfg.gamma = 5.0 / 3.0;
   for (int f = 0; f < 6; f++) { cfg.bc[f] = EULERB200_BC_REFLECTING; cfg.nbr[f] = EULERB200_NO_NEIGHBOR; }
   eb::RhsParams P;
-  P.nx = P.ny = P.nz = n; P.nchem = nchem; P.gamma = cfg.gamma; P.rdx = P.rdy = P.rdz = (double)n; P.dx = P.dy = P.dz = 1.0 / n;
+  P.nx = P.ny = P.nz = n; P.nchem = nchem; P.gamma = cfg.gamma; P.rdx = P.rdy = P.rdz = EB_RD_SCALE * (double)n; P.dx = P.dy = P.dz = 1.0 / n;
   for (int f = 0; f < 5; f++) P.forcing[f] = 0.0;
   for (int f = 0; f < 6; f++) { P.w[f] = w[f]; P.wdot[f] = wd[f]; eb::ghost_face(cfg, f, nullptr, &P.ghost[f]); }
   for (int q = 0; q < 4; q++) P.aux[q] = aux[q];
