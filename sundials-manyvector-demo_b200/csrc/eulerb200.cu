@@ -172,6 +172,7 @@ struct eulerb200_ctx {
   int variant = 0;
   int split = 0;                 // EULERB200_SPLIT=1: fluid fields and species in separate launches
   int stage = 0;                 // EULERB200_STAGE=1: the bulk-copy staging variant of the fused kernel (A/B)
+  long long halo_timeout_cycles = 20000000000LL;   // peer-store halo wait: EULERB200_HALO_TIMEOUT_S (default 10 s) x the SM clock rate
   int overlap = 1;               // EULERB200_OVERLAP: 1 interior launch behind the halo exchange, then the shell launches;
                                  // 2 shells on high-priority streams as soon as the halo is in; 0 exchange first, one launch (rhs_impl)
   bool prof_pack_first = false;
@@ -469,7 +470,7 @@ int exchange_end(eulerb200_ctx* c, cudaStream_t s)
     unsigned mask = 0;
     for (int f = 0; f < 6; f++) if (c->remote[f]) mask |= 1u << f;
     halo_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const unsigned long long*>(c->mailbox + c->arrival_off), mask,
-                                      c->seq, 20000000000LL /* ~10 s */, c->d_flag);
+                                      c->seq, c->halo_timeout_cycles, c->d_flag);
     c->launches++;
     EB_CUDA(c, cudaGetLastError());
   } else {
@@ -571,6 +572,15 @@ int eulerb200_create(const eulerb200_config* cfg, eulerb200_ctx** out)
     if (e != cudaSuccess) { delete c; return fail(nullptr, -2, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
   }
   cudaGetDevice(&c->device);
+  {
+    // how long a rank may wait for a neighbour's ghost layers before the right-hand side fails with -3 (a rank
+    // stalled for longer, e.g. on I/O, is a hard failure): seconds from the environment, cycles from the clock rate
+    double secs = 10.0;
+    if (const char* ev = getenv("EULERB200_HALO_TIMEOUT_S")) secs = std::max(0.001, atof(ev));
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device) != cudaSuccess || khz <= 0) khz = 2000000;
+    c->halo_timeout_cycles = (long long)(secs * 1e3 * (double)khz);
+  }
 #define EB_CREATE(call)                                                                   \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
@@ -797,6 +807,20 @@ int eulerb200_rhs_async(eulerb200_ctx* c, double t, const double* const* w, doub
   return rhs_impl(c, w, wdot, stream, 0, 1.0);
 }
 
+// What the device flag of a right-hand side says, for every entry point that reads it back (rhs, rhs_slow,
+// rhs_host; the async path hands the raw bits to eulerb200_state_flag's caller): bit 8 = a rank's peer-store
+// halo wait timed out (communication error, -3), bits 1 / 2 / 4 = legal_state (euler3D.hpp:1405-1414, -1).
+static int decode_flag(eulerb200_ctx* c, int32_t bits)
+{
+  if (bits & 8) return fail(c, -3, "halo exchange timed out waiting for a neighbour's ghost layers (peer-store transport)");
+  if (bits) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
+    return fail(c, -1, msg);
+  }
+  return 0;
+}
+
 int eulerb200_rhs_slow(eulerb200_ctx* c, double t, double* const* w, double* const* wdot, double energy_units,
                        void* stream)
 {
@@ -809,12 +833,7 @@ int eulerb200_rhs_slow(eulerb200_ctx* c, double t, double* const* w, double* con
   int32_t bits = 0;
   rc = eulerb200_state_flag(c, stream, &bits);
   if (rc) return rc;
-  if (bits) {
-    char msg[160];
-    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
-    return fail(c, -1, msg);
-  }
-  return 0;
+  return decode_flag(c, bits);
 }
 
 static int profile_collect(eulerb200_ctx* c)
@@ -983,13 +1002,7 @@ int eulerb200_rhs(eulerb200_ctx* c, double t, const double* const* w, double* co
   int32_t bits = 0;
   rc = eulerb200_state_flag(c, stream, &bits);
   if (rc) return rc;
-  if (bits & 8) return fail(c, -3, "halo exchange timed out waiting for a neighbour's ghost layers (peer-store transport)");
-  if (bits) {
-    char msg[160];
-    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
-    return fail(c, -1, msg);
-  }
-  return 0;
+  return decode_flag(c, bits);
 }
 
 int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, double* const* wdh)
@@ -1058,12 +1071,7 @@ int eulerb200_rhs_host(eulerb200_ctx* c, double t, const double* const* wh, doub
   int32_t bits = 0;
   int rc = eulerb200_state_flag(c, c->s_cmp, &bits);
   if (rc) return rc;
-  if (bits) {
-    char msg[160];
-    snprintf(msg, sizeof msg, "STATE_ERROR: legal_state (fEuler) failed with flag = %d (1 density, 2 energy, 4 pressure)", bits);
-    return fail(c, -1, msg);
-  }
-  return 0;
+  return decode_flag(c, bits);
 }
 
 int eulerb200_rhs_any(eulerb200_ctx* c, double t, const double* const* w, double* const* wdot, void* stream)

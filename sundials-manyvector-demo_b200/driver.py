@@ -268,8 +268,10 @@ class ERKStep:
                     return -1, self.t
                 eta = min(self.etamxf if nef >= 2 else 1.0, max(0.1, self._eta_pid(dsm)))
                 h *= eta
-            # accept
-            self.w, self.ytmp = self.ytmp, self.w
+            # accept: the two vectors trade their sub-vector lists, not their identities, so that the ManyVector the
+            # caller handed to the constructor holds the solution after evolve() as ARKStepEvolve's does (a caller
+            # that kept one of its sub-vector tensors must re-read w.sub)
+            self.w.sub, self.ytmp.sub = self.ytmp.sub, self.w.sub
             self.t += h
             self.nst += 1
             steps_here += 1

@@ -341,7 +341,8 @@ int main(int argc, char** argv)
         printf(" %9.1e", sqrt(s / N));
       }
       if (P.nchem > 0) {
-        if (!write_files) eulerb200_copy_to_host(host_chem.data(), S.w.sub[5], sizeof(double) * N * P.nchem);
+        // (always: write_file() runs AFTER stats() in the output loop, its copy is one output old here)
+        eulerb200_copy_to_host(host_chem.data(), S.w.sub[5], sizeof(double) * N * P.nchem);
         for (int v = 0; v < P.nchem; v++) {
           double s = 0;
           for (long c = 0; c < N; c++) s += host_chem[c * P.nchem + v] * host_chem[c * P.nchem + v];

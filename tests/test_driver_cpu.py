@@ -44,10 +44,13 @@ def test_linear_advection_with_oracle_rhs(pkg, port, axis):
         parts, d = advection_state(n, axis)
         ops = OracleVecOps(port, None, n, 0, d, 1.4, [P] * 6)
         opts = pkg.driver.ARKODEParameters(order=4, rtol=1e-9, atol=1e-12)
-        step = pkg.driver.ERKStep(ops, 0.0, NpVec(parts), opts)
+        w = NpVec(parts)
+        step = pkg.driver.ERKStep(ops, 0.0, w, opts)
         mass0, en0 = parts[0].sum(), parts[4].sum()
         ret, t = step.evolve(0.25)
         assert ret == 0 and t == 0.25
+        # the vector handed to the constructor holds the solution afterwards, as ARKStepEvolve's does
+        assert step.w is w and all(a is b for a, b in zip(w.sub, step.w.sub))
         true, _ = advection_state(n, axis, t=0.25)
         errs.append(max(np.abs(step.w.sub[0] - true[0]).max(), 1e-300))
         assert abs(step.w.sub[0].sum() - mass0) <= 1e-13 * mass0
