@@ -53,6 +53,15 @@ class Emu:
         c.rank, c.nranks = rank, 1
         return c
 
+    def face_flux(self, w1d, idir, gamma):
+        """One face through the product's face arithmetic on the reference's face_flux interface
+        (utilities.cpp:270): w1d[6][nvar] -> f_face[nvar]."""
+        w1d = np.ascontiguousarray(w1d, dtype=np.float64)
+        nvar = w1d.shape[1]
+        out = np.empty(nvar)
+        self.lib.emu_face_flux(w1d.ctypes.data_as(_dp), nvar, int(idir), C.c_double(gamma), out.ctypes.data_as(_dp))
+        return out
+
     def face(self, what, n, nchem, bcs, nbr, rank, w, f, recv=None):
         """what = 'pack': the send buffer of face f (pack_face_kernel); 'ghost': the ghost layers of
         face f in the reference's receive-buffer layout (ghost_face_kernel)."""

@@ -191,3 +191,35 @@ extern "C" void emu_wrms_accum(const double* x, const double* y, double rtol, do
   WrmsArgs a = {x, y, rtol, atol, n, acc};
   cuda_emu::launch(wrms_entry, dim3(emu_blocks(n)), dim3(64), 0, a);
 }
+
+// One face through the product's face arithmetic (euler_math.cuh: cell_aux, fluid_face, tracer_face) on the
+// reference's own face_flux interface: w1d[6][nvar] in the reference's field order, idir, f_face[nvar]
+// (utilities.cpp:270).  The stencil is put into sweep-aligned order and the fluxes back exactly as face_all does.
+extern "C" void emu_face_flux(const double* w1d, int nvar, int idir, double gamma, double* f_face)
+{
+#ifndef EB_STRICT
+  const int fn = 1 + idir, f1 = (idir == 1) ? 1 : 2, f2 = (idir == 2) ? 1 : 3;
+  eb::FluidStencil s;
+  for (int l = 0; l < 6; l++) {
+    const double* c = w1d + (long)l * nvar;
+    s.r[l] = c[0]; s.mn[l] = c[fn]; s.m1[l] = c[f1]; s.m2[l] = c[f2]; s.e[l] = c[4];
+    const eb::CellAux a = eb::cell_aux(gamma, s.r[l], s.mn[l], s.m1[l], s.m2[l], s.e[l]);
+    s.rinv[l] = a.rinv; s.p[l] = a.p; s.c[l] = a.c;
+    if (l == 2) s.srL = a.sr;
+    if (l == 3) s.srR = a.sr;
+  }
+  double f[5], alpha, u[6];
+  eb::fluid_face(s, gamma, f, alpha, u);
+  const double half = EB_FOLD_HALF ? 0.5 : 1.0;       // the faces hand out twice the flux where the divergence halves it
+  f_face[0] = half * f[0]; f_face[fn] = half * f[1]; f_face[f1] = half * f[2]; f_face[f2] = half * f[3]; f_face[4] = half * f[4];
+  double up[6], um[6];
+  for (int l = 0; l < 6; l++) { up[l] = u[l] + alpha; um[l] = u[l] - alpha; }
+  for (int v = 5; v < nvar; v++) {
+    double c[6];
+    for (int l = 0; l < 6; l++) c[l] = w1d[(long)l * nvar + v];
+    f_face[v] = half * eb::tracer_face(c, up, um);
+  }
+#else
+  (void)w1d; (void)nvar; (void)idir; (void)gamma; (void)f_face;
+#endif
+}

@@ -51,6 +51,22 @@ def test_emulated_kernel_matches_oracle(emu, oracle_mod, port, n, nchem, bcs, th
     assert ret == 0 and max(normwise_errors(got3, ref, floor)) <= 1e-12
 
 
+@pytest.mark.parametrize("nvar", [5, 15])
+def test_face_arithmetic_vs_reference_face_flux_golden(emu, nvar):
+    """SURVEY.md 8(a2) face by face: the product's face arithmetic (euler_math.cuh: cell_aux, fluid_face,
+    tracer_face -- the re-derived formulation, not face_flux recompiled) against the 60 + 60 faces the unmodified
+    reference's face_flux produced (tests/golden/face_flux_nvar*.npz, all three directions), per field relative to
+    the largest flux of that field: a flux is a sum of O(1) terms, no divergence has cancelled anything yet, so
+    the distance is a few ulps (measured 6.5e-16 at NVAR = 5, 5.8e-15 at NVAR = 15) -- the bar here is 1e-14."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "face_flux_nvar%d.npz" % nvar))
+    got = np.array([emu.face_flux(s, int(idir), float(z["gamma"])) for s, idir in zip(z["stencil"], z["idir"])])
+    ref = np.array(z["flux"])
+    assert sorted(set(int(d) for d in z["idir"])) == [0, 1, 2]
+    err = np.abs(got - ref).max(axis=0) / np.abs(ref).max(axis=0)
+    assert err.max() <= 1e-14, err
+
+
 def _golden_ids():
     import os
     from test_oracle import FEULER_FILES
